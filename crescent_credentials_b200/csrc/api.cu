@@ -1,0 +1,700 @@
+// api.cu -- extern "C" entry points of libg16b200.so (declared in include/g16_b200.h) and the prove orchestration:
+// stream fork/join of the witness map, the five MSMs and the assembly, mirroring
+// Groth16::create_proof_with_reduction_and_matrices (forks/groth16/src/prover.rs:26-51).
+#include <stdarg.h>
+#include <string.h>
+
+#include "internal.cuh"
+
+using namespace g16;
+
+static thread_local std::string g_create_err;
+
+namespace g16 {
+int set_err(g16_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_err = buf;
+    return code;
+}
+}  // namespace g16
+
+// MSM order used throughout: 0 = h, 1 = l, 2 = a, 3 = b_g1, 4 = b_g2
+enum { Q_H = 0, Q_L = 1, Q_A = 2, Q_B1 = 3, Q_B2 = 4 };
+
+struct Guard {
+    g16_ctx* c;
+    explicit Guard(g16_ctx* ctx) : c(ctx) {
+        c->mu.lock();
+        cudaSetDevice(c->device);
+    }
+    ~Guard() { c->mu.unlock(); }
+};
+
+extern "C" {
+
+const char* g16_version(void) { return "g16-b200 0.1 (sm_100a)"; }
+
+int g16_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* g16_last_error(const g16_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int g16_ctx_create(g16_ctx** out, int device, void* main_stream) {
+    if (!out) return set_err(nullptr, G16_ERR_BAD_ARG, "g16_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = g16_device_count();
+    if (n <= 0) return set_err(nullptr, G16_ERR_NO_DEVICE, "no CUDA device visible: libg16b200 has no CPU fallback");
+    if (device < 0 || device >= n) return set_err(nullptr, G16_ERR_BAD_ARG, "device %d out of range (%d visible)", device, n);
+    g16_ctx* ctx = new g16_ctx();
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return set_err(nullptr, G16_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    }
+    if (main_stream) {
+        ctx->main = (cudaStream_t)main_stream;
+        ctx->own_main = false;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking);
+        ctx->own_main = true;
+    }
+    for (int i = 0; i < kSideStreams && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev_t[i]);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_small, 4096);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_partial, sizeof(g16_partial));
+    if (e != cudaSuccess) {
+        int rc = set_err(nullptr, e == cudaErrorMemoryAllocation ? G16_ERR_OOM : G16_ERR_CUDA, "context setup: %s",
+                         cudaGetErrorString(e));
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return G16_OK;
+}
+
+static void free_r1cs(g16_ctx* ctx) {
+    for (int k = 0; k < 3; k++) {
+        dev_free(ctx->mat[k].row_ptr);
+        dev_free(ctx->mat[k].col);
+        dev_free(ctx->mat[k].val);
+        ctx->mat[k] = CsrDev();
+    }
+    dev_free(ctx->d_z);
+    dev_free(ctx->d_a);
+    dev_free(ctx->d_b);
+    dev_free(ctx->d_c);
+    ctx->d_z = ctx->d_a = ctx->d_b = ctx->d_c = nullptr;
+    ctx->have_r1cs = false;
+    ctx->witness_resident = false;
+}
+
+void g16_ctx_destroy(g16_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_r1cs(ctx);
+    for (int k = 0; k < 5; k++) msm_free(&ctx->q[k], &ctx->scratch[k]);
+    for (int k = 0; k < kMsmSlots; k++) msm_free(&ctx->slot[k], &ctx->slot_scratch[k]);
+    for (auto& kv : ctx->ntt) {
+        dev_free(kv.second.tw);
+        dev_free(kv.second.tw_inv);
+        dev_free(kv.second.coset);
+        dev_free(kv.second.coset_inv);
+        dev_free(kv.second.coset_scaled);
+        dev_free(kv.second.odd_scaled);
+    }
+    dev_free(ctx->d_small);
+    dev_free(ctx->d_partial);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int i = 0; i < kSideStreams; i++) {
+        if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int i = 0; i < 16; i++)
+        if (ctx->ev_t[i]) cudaEventDestroy(ctx->ev_t[i]);
+    if (ctx->own_main && ctx->main) cudaStreamDestroy(ctx->main);
+    delete ctx;
+}
+
+uint64_t g16_launch_count(const g16_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int g16_sync(g16_ctx* ctx) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    return G16_OK;
+}
+
+// ---- device memory ----------------------------------------------------------------------------------------------------
+int g16_dev_alloc(g16_ctx* ctx, size_t bytes, void** p) {
+    if (!ctx || !p) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_CUDA(ctx, cudaMalloc(p, bytes ? bytes : 1));
+    return G16_OK;
+}
+int g16_dev_free(g16_ctx* ctx, void* p) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_CUDA(ctx, cudaFree(p));
+    return G16_OK;
+}
+int g16_dev_upload(g16_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->main));
+    G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    return G16_OK;
+}
+int g16_dev_download(g16_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->main));
+    G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    return G16_OK;
+}
+
+// ---- building blocks ----------------------------------------------------------------------------------------------------
+int g16_field_op(g16_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    if (!ctx || !a || !out) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "field_op: null pointer") : G16_ERR_BAD_ARG;
+    bool binary = (op == G16_OP_MUL || op == G16_OP_ADD || op == G16_OP_SUB);
+    if (binary && !b) return set_err(ctx, G16_ERR_BAD_ARG, "field_op: binary op needs b");
+    if (n == 0) return G16_OK;
+    Guard g(ctx);
+    size_t esz = field == G16_FIELD_FQ2 ? 64 : 32;
+    void *da = nullptr, *db = nullptr, *dc = nullptr;
+    G16_CUDA(ctx, cudaMalloc(&da, n * esz));
+    G16_CUDA(ctx, cudaMalloc(&db, n * esz));
+    G16_CUDA(ctx, cudaMalloc(&dc, n * esz));
+    int rc = G16_OK;
+    cudaMemcpyAsync(da, a, n * esz, cudaMemcpyHostToDevice, ctx->main);
+    if (binary) cudaMemcpyAsync(db, b, n * esz, cudaMemcpyHostToDevice, ctx->main);
+    rc = field_op_dev(ctx, field, op, da, db, dc, n, ctx->main);
+    if (rc == G16_OK) {
+        cudaMemcpyAsync(out, dc, n * esz, cudaMemcpyDeviceToHost, ctx->main);
+        cudaError_t e = cudaStreamSynchronize(ctx->main);
+        if (e != cudaSuccess) rc = set_err(ctx, G16_ERR_CUDA, "field_op: %s", cudaGetErrorString(e));
+    }
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dc);
+    return rc;
+}
+
+int g16_bench_int_pipe(g16_ctx* ctx, int which, double* gops) {
+    if (!ctx || !gops) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    return bench_int_pipe(ctx, which, gops);
+}
+
+int g16_ntt_dev(g16_ctx* ctx, void* data_dev, unsigned log_n, int inverse, int coset) {
+    if (!ctx || !data_dev) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    return ntt_api(ctx, (Fr*)data_dev, log_n, inverse, coset, ctx->main);
+}
+
+int g16_ntt(g16_ctx* ctx, uint64_t* data, unsigned log_n, int inverse, int coset) {
+    if (!ctx || !data) return G16_ERR_BAD_ARG;
+    if (log_n > 28) return set_err(ctx, G16_ERR_DEGREE_TOO_LARGE, "domain 2^%u exceeds Fr two-adicity 28", log_n);
+    Guard g(ctx);
+    size_t bytes = ((size_t)32) << log_n;
+    Fr* d;
+    G16_CUDA(ctx, cudaMalloc((void**)&d, bytes));
+    cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, ctx->main);
+    int rc = ntt_api(ctx, d, log_n, inverse, coset, ctx->main);
+    if (rc == G16_OK) {
+        cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, ctx->main);
+        cudaError_t e = cudaStreamSynchronize(ctx->main);
+        if (e != cudaSuccess) rc = set_err(ctx, G16_ERR_CUDA, "ntt: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+static int msm_host(g16_ctx* ctx, int group, const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t* out,
+                    int* out_inf) {
+    if (!ctx || !out || (n && (!points || !scalars))) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "msm: null pointer") : G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    size_t pb = group == 1 ? 64 : 128;
+    if (n == 0) {
+        memset(out, 0, pb);
+        if (out_inf) *out_inf = 1;
+        return G16_OK;
+    }
+    void* dp = nullptr;
+    Fr* ds = nullptr;
+    G16_CUDA(ctx, cudaMalloc(&dp, n * pb));
+    G16_CUDA(ctx, cudaMalloc((void**)&ds, n * 32));
+    cudaMemcpyAsync(dp, points, n * pb, cudaMemcpyHostToDevice, ctx->main);
+    cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, ctx->main);
+    MsmBases mb;
+    MsmScratch sc;
+    int rc = msm_set_bases(ctx, &mb, &sc, group, dp, n, 0, false, ctx->main);
+    if (rc == G16_OK) rc = msm_run(ctx, &mb, &sc, ds, n, ctx->main);
+    if (rc == G16_OK) rc = xyzz_to_affine_host(ctx, group, sc.result, out, out_inf, ctx->main);
+    cudaStreamSynchronize(ctx->main);
+    msm_free(&mb, &sc);
+    cudaFree(dp);
+    cudaFree(ds);
+    return rc;
+}
+int g16_msm_g1(g16_ctx* ctx, const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t out[8], int* out_inf) {
+    return msm_host(ctx, 1, points, scalars, n, out, out_inf);
+}
+int g16_msm_g2(g16_ctx* ctx, const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t out[16], int* out_inf) {
+    return msm_host(ctx, 2, points, scalars, n, out, out_inf);
+}
+
+int g16_msm_set_bases_dev(g16_ctx* ctx, int slot, int group, const void* points_dev, size_t n, int window_bits, int precompute) {
+    if (!ctx || slot < 0 || slot >= kMsmSlots) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "msm slot out of range") : G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_TRY(msm_set_bases(ctx, &ctx->slot[slot], &ctx->slot_scratch[slot], group, points_dev, n, window_bits, precompute != 0,
+                          ctx->main));
+    G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    return G16_OK;
+}
+int g16_msm_set_bases(g16_ctx* ctx, int slot, int group, const uint64_t* points, size_t n, int window_bits, int precompute) {
+    if (!ctx || (n && !points)) return G16_ERR_BAD_ARG;
+    if (group != 1 && group != 2) return set_err(ctx, G16_ERR_BAD_ARG, "group must be 1 or 2");
+    size_t pb = group == 1 ? 64 : 128;
+    void* dp = nullptr;
+    {
+        Guard g(ctx);
+        G16_CUDA(ctx, cudaMalloc(&dp, n ? n * pb : 1));
+        G16_CUDA(ctx, cudaMemcpy(dp, points, n * pb, cudaMemcpyHostToDevice));
+    }
+    int rc = g16_msm_set_bases_dev(ctx, slot, group, dp, n, window_bits, precompute);
+    cudaFree(dp);
+    return rc;
+}
+int g16_msm_run_dev(g16_ctx* ctx, int slot, const void* scalars_dev, size_t n, uint64_t* out, int* out_inf) {
+    if (!ctx || slot < 0 || slot >= kMsmSlots) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "msm slot out of range") : G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    MsmBases* mb = &ctx->slot[slot];
+    if (mb->group == 0) return set_err(ctx, G16_ERR_BAD_ARG, "msm slot %d has no bases", slot);
+    G16_TRY(msm_run(ctx, mb, &ctx->slot_scratch[slot], (const Fr*)scalars_dev, n, ctx->main));
+    if (out) return xyzz_to_affine_host(ctx, mb->group, ctx->slot_scratch[slot].result, out, out_inf, ctx->main);
+    return G16_OK;
+}
+
+static int fixed_base_host(g16_ctx* ctx, int group, const uint64_t* scalars, size_t n, uint64_t* out) {
+    if (!ctx || (n && (!scalars || !out))) return G16_ERR_BAD_ARG;
+    if (n == 0) return G16_OK;
+    Guard g(ctx);
+    size_t pb = group == 1 ? 64 : 128;
+    Fr* ds;
+    void* dp;
+    G16_CUDA(ctx, cudaMalloc((void**)&ds, n * 32));
+    G16_CUDA(ctx, cudaMalloc(&dp, n * pb));
+    cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, ctx->main);
+    int rc = fixed_base_dev(ctx, group, ds, n, dp, ctx->main);
+    if (rc == G16_OK) {
+        cudaMemcpyAsync(out, dp, n * pb, cudaMemcpyDeviceToHost, ctx->main);
+        cudaError_t e = cudaStreamSynchronize(ctx->main);
+        if (e != cudaSuccess) rc = set_err(ctx, G16_ERR_CUDA, "fixed_base: %s", cudaGetErrorString(e));
+    }
+    cudaFree(ds);
+    cudaFree(dp);
+    return rc;
+}
+int g16_fixed_base_g1(g16_ctx* ctx, const uint64_t* scalars, size_t n, uint64_t* out) { return fixed_base_host(ctx, 1, scalars, n, out); }
+int g16_fixed_base_g2(g16_ctx* ctx, const uint64_t* scalars, size_t n, uint64_t* out) { return fixed_base_host(ctx, 2, scalars, n, out); }
+int g16_fixed_base_g1_dev(g16_ctx* ctx, const void* s, size_t n, void* out) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    return fixed_base_dev(ctx, 1, (const Fr*)s, n, out, ctx->main);
+}
+int g16_fixed_base_g2_dev(g16_ctx* ctx, const void* s, size_t n, void* out) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    return fixed_base_dev(ctx, 2, (const Fr*)s, n, out, ctx->main);
+}
+
+// ---- R1CS -------------------------------------------------------------------------------------------------------------------
+int g16_ctx_load_r1cs(g16_ctx* ctx, const g16_r1cs_view* v) {
+    if (!ctx || !v) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (v->num_instance == 0 || v->num_instance > v->num_wires)
+        return set_err(ctx, G16_ERR_BAD_ARG, "r1cs: num_instance %llu / num_wires %llu inconsistent",
+                       (unsigned long long)v->num_instance, (unsigned long long)v->num_wires);
+    if (v->num_wires >= ((uint64_t)1 << 32)) return set_err(ctx, G16_ERR_BAD_ARG, "r1cs: more than 2^32 wires");
+    // domain: smallest power of two >= num_constraints + num_instance (r1cs_to_qap.rs:156-158)
+    uint64_t need = v->num_constraints + v->num_instance;
+    unsigned log_n = 0;
+    while (((uint64_t)1 << log_n) < need) log_n++;
+    if (log_n > 28) return set_err(ctx, G16_ERR_DEGREE_TOO_LARGE, "domain size %llu exceeds 2^28", (unsigned long long)need);
+    for (int k = 0; k < 3; k++) {
+        if (v->num_constraints && (!v->row_ptr[k])) return set_err(ctx, G16_ERR_BAD_ARG, "r1cs: null row_ptr");
+        uint64_t nnz = v->num_constraints ? v->row_ptr[k][v->num_constraints] : 0;
+        if (nnz && (!v->col[k] || !v->val[k])) return set_err(ctx, G16_ERR_BAD_ARG, "r1cs: null col/val");
+        if (v->num_constraints && v->row_ptr[k][0] != 0) return set_err(ctx, G16_ERR_BAD_ARG, "r1cs: row_ptr[0] != 0");
+        for (uint64_t i = 0; i < v->num_constraints; i++)
+            if (v->row_ptr[k][i + 1] < v->row_ptr[k][i]) return set_err(ctx, G16_ERR_BAD_ARG, "r1cs: row_ptr not monotone");
+        for (uint64_t j = 0; j < nnz; j++)
+            if (v->col[k][j] >= v->num_wires) return set_err(ctx, G16_ERR_BAD_ARG, "r1cs: column index out of range");
+    }
+    free_r1cs(ctx);
+    ctx->nc = v->num_constraints;
+    ctx->ni = v->num_instance;
+    ctx->m = v->num_wires;
+    ctx->log_n = log_n;
+    size_t n = (size_t)1 << log_n;
+    for (int k = 0; k < 3; k++) {
+        uint64_t nnz = ctx->nc ? v->row_ptr[k][ctx->nc] : 0;
+        ctx->mat[k].nnz = nnz;
+        G16_TRY(dev_alloc(ctx, &ctx->mat[k].row_ptr, ctx->nc + 1));
+        G16_TRY(dev_alloc(ctx, &ctx->mat[k].col, nnz));
+        G16_TRY(dev_alloc(ctx, &ctx->mat[k].val, nnz));
+        if (ctx->nc) G16_CUDA(ctx, cudaMemcpyAsync(ctx->mat[k].row_ptr, v->row_ptr[k], (ctx->nc + 1) * 8, cudaMemcpyHostToDevice, ctx->main));
+        else G16_CUDA(ctx, cudaMemsetAsync(ctx->mat[k].row_ptr, 0, 8, ctx->main));
+        if (nnz) {
+            G16_CUDA(ctx, cudaMemcpyAsync(ctx->mat[k].col, v->col[k], nnz * 4, cudaMemcpyHostToDevice, ctx->main));
+            G16_CUDA(ctx, cudaMemcpyAsync(ctx->mat[k].val, v->val[k], nnz * 32, cudaMemcpyHostToDevice, ctx->main));
+            if (v->encoding == G16_ENC_CANONICAL) G16_TRY(convert_mont_dev(ctx, G16_FIELD_FR, ctx->mat[k].val, nnz, true, ctx->main));
+        }
+    }
+    G16_TRY(dev_alloc(ctx, &ctx->d_z, ctx->m));
+    G16_TRY(dev_alloc(ctx, &ctx->d_a, n));
+    G16_TRY(dev_alloc(ctx, &ctx->d_b, n));
+    G16_TRY(dev_alloc(ctx, &ctx->d_c, n));
+    NttTables* t;
+    G16_TRY(ntt_get_tables(ctx, log_n, &t));
+    G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    ctx->have_r1cs = true;
+    return G16_OK;
+}
+
+int g16_domain_size(g16_ctx* ctx, size_t* n_out) {
+    if (!ctx || !n_out) return G16_ERR_BAD_ARG;
+    if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "no R1CS loaded");
+    *n_out = (size_t)1 << ctx->log_n;
+    return G16_OK;
+}
+
+static int upload_witness(g16_ctx* ctx, const uint64_t* z, cudaStream_t st) {
+    if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "no R1CS loaded");
+    if (!z) return set_err(ctx, G16_ERR_BAD_ARG, "witness pointer is NULL");
+    G16_CUDA(ctx, cudaMemcpyAsync(ctx->d_z, z, ctx->m * 32, cudaMemcpyHostToDevice, st));
+    ctx->witness_resident = true;
+    return G16_OK;
+}
+
+int g16_upload_witness(g16_ctx* ctx, const uint64_t* z) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_TRY(upload_witness(ctx, z, ctx->main));
+    G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    return G16_OK;
+}
+
+int g16_r1cs_eval(g16_ctx* ctx, const uint64_t* z, uint64_t* az, uint64_t* bz, uint64_t* cz) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_TRY(upload_witness(ctx, z, ctx->main));
+    size_t n = (size_t)1 << ctx->log_n;
+    G16_CUDA(ctx, cudaMemsetAsync(ctx->d_a, 0, n * 32, ctx->main));
+    G16_CUDA(ctx, cudaMemsetAsync(ctx->d_b, 0, n * 32, ctx->main));
+    G16_CUDA(ctx, cudaMemsetAsync(ctx->d_c, 0, n * 32, ctx->main));
+    G16_TRY(r1cs_eval_dev(ctx, az ? ctx->d_a : nullptr, bz ? ctx->d_b : nullptr, cz ? ctx->d_c : nullptr, false, ctx->main));
+    if (az) G16_CUDA(ctx, cudaMemcpyAsync(az, ctx->d_a, ctx->nc * 32, cudaMemcpyDeviceToHost, ctx->main));
+    if (bz) G16_CUDA(ctx, cudaMemcpyAsync(bz, ctx->d_b, ctx->nc * 32, cudaMemcpyDeviceToHost, ctx->main));
+    if (cz) G16_CUDA(ctx, cudaMemcpyAsync(cz, ctx->d_c, ctx->nc * 32, cudaMemcpyDeviceToHost, ctx->main));
+    G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    return G16_OK;
+}
+
+int g16_witness_map(g16_ctx* ctx, const uint64_t* z, int reduction, uint64_t* h_out, size_t h_capacity, size_t* n_out) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "no R1CS loaded");
+    size_t n = (size_t)1 << ctx->log_n;
+    if (n_out) *n_out = n;
+    if (!h_out || h_capacity < n) return set_err(ctx, G16_ERR_BAD_ARG, "witness_map: h buffer holds %zu < %zu elements", h_capacity, n);
+    G16_TRY(upload_witness(ctx, z, ctx->main));
+    G16_TRY(witness_map_dev(ctx, reduction, ctx->main));
+    G16_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_a, n * 32, cudaMemcpyDeviceToHost, ctx->main));
+    G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    return G16_OK;
+}
+
+// ---- proving key ---------------------------------------------------------------------------------------------------------------
+static void load_fq(Fq* dst, const uint64_t* src, int count, int enc) {
+    for (int k = 0; k < count; k++) {
+        Fq x;
+        for (int i = 0; i < 4; i++) {
+            x.v[2 * i] = (uint32_t)src[4 * k + i];
+            x.v[2 * i + 1] = (uint32_t)(src[4 * k + i] >> 32);
+        }
+        dst[k] = enc == G16_ENC_CANONICAL ? x.to_mont() : x;
+    }
+}
+
+// uploads points [lo, hi) of a host query (skipping `skip_first` leading points) into an MSM base set
+static int load_query(g16_ctx* ctx, int qi, int group, const uint64_t* pts, size_t total, size_t lo, size_t hi, int enc,
+                      int precompute) {
+    size_t pb = group == 1 ? 64 : 128;
+    size_t cnt = hi - lo;
+    ctx->pk_len[qi] = total;
+    ctx->sh_lo[qi] = lo;
+    ctx->sh_hi[qi] = hi;
+    void* stage = nullptr;
+    G16_CUDA(ctx, cudaMalloc(&stage, cnt ? cnt * pb : 1));
+    int rc = G16_OK;
+    if (cnt) {
+        cudaError_t e = cudaMemcpyAsync(stage, (const char*)pts + lo * pb, cnt * pb, cudaMemcpyHostToDevice, ctx->main);
+        if (e != cudaSuccess) rc = set_err(ctx, G16_ERR_CUDA, "pk upload: %s", cudaGetErrorString(e));
+        if (rc == G16_OK && enc == G16_ENC_CANONICAL) rc = convert_mont_dev(ctx, G16_FIELD_FQ, stage, cnt * (pb / 32), true, ctx->main);
+    }
+    if (rc == G16_OK) rc = msm_set_bases(ctx, &ctx->q[qi], &ctx->scratch[qi], group, stage, cnt, 0, precompute != 0, ctx->main);
+    cudaStreamSynchronize(ctx->main);
+    cudaFree(stage);
+    return rc;
+}
+
+int g16_ctx_load_pk(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int shard_count, int precompute) {
+    if (!ctx || !pk) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count)
+        return set_err(ctx, G16_ERR_BAD_ARG, "shard %d of %d is not a valid rank", shard_rank, shard_count);
+    if (!pk->alpha_g1 || !pk->beta_g1 || !pk->delta_g1 || !pk->beta_g2 || !pk->delta_g2)
+        return set_err(ctx, G16_ERR_BAD_ARG, "pk: a single-point pointer is NULL");
+    if (pk->a_len == 0 || pk->b_g1_len != pk->a_len || pk->b_g2_len != pk->a_len)
+        return set_err(ctx, G16_ERR_BAD_ARG, "pk: a/b_g1/b_g2 query lengths %zu/%zu/%zu must be equal and non-zero", pk->a_len,
+                       pk->b_g1_len, pk->b_g2_len);
+    if (!pk->a_query || !pk->b_g1_query || !pk->b_g2_query || (pk->h_len && !pk->h_query) || (pk->l_len && !pk->l_query))
+        return set_err(ctx, G16_ERR_BAD_ARG, "pk: a query pointer is NULL");
+    ctx->have_pk = false;
+    ctx->shard_rank = shard_rank;
+    ctx->shard_count = shard_count;
+    int enc = pk->encoding;
+    load_fq(&ctx->alpha_g1.x, pk->alpha_g1, 2, enc);
+    load_fq(&ctx->beta_g1.x, pk->beta_g1, 2, enc);
+    load_fq(&ctx->delta_g1.x, pk->delta_g1, 2, enc);
+    load_fq(&ctx->beta_g2.x.c0, pk->beta_g2, 4, enc);
+    load_fq(&ctx->delta_g2.x.c0, pk->delta_g2, 4, enc);
+    load_fq(&ctx->a0.x, pk->a_query, 2, enc);          // query[0]: the constant-1 wire (prover.rs:265)
+    load_fq(&ctx->b1_0.x, pk->b_g1_query, 2, enc);
+    load_fq(&ctx->b2_0.x.c0, pk->b_g2_query, 4, enc);
+    auto range = [&](size_t total, size_t* lo, size_t* hi) {
+        *lo = total * (size_t)shard_rank / (size_t)shard_count;
+        *hi = total * (size_t)(shard_rank + 1) / (size_t)shard_count;
+    };
+    size_t lo, hi;
+    range(pk->h_len, &lo, &hi);
+    G16_TRY(load_query(ctx, Q_H, 1, pk->h_query, pk->h_len, lo, hi, enc, precompute));
+    range(pk->l_len, &lo, &hi);
+    G16_TRY(load_query(ctx, Q_L, 1, pk->l_query, pk->l_len, lo, hi, enc, precompute));
+    size_t m1 = pk->a_len - 1;  // MSM over query[1..] (prover.rs:266)
+    range(m1, &lo, &hi);
+    G16_TRY(load_query(ctx, Q_A, 1, pk->a_query + 8, m1, lo, hi, enc, precompute));
+    G16_TRY(load_query(ctx, Q_B1, 1, pk->b_g1_query + 8, m1, lo, hi, enc, precompute));
+    G16_TRY(load_query(ctx, Q_B2, 2, pk->b_g2_query + 16, m1, lo, hi, enc, precompute));
+    ctx->have_pk = true;
+    return G16_OK;
+}
+
+// ---- prove ------------------------------------------------------------------------------------------------------------------------
+static int check_ready(g16_ctx* ctx) {
+    if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "prove: no R1CS loaded");
+    if (!ctx->have_pk) return set_err(ctx, G16_ERR_BAD_ARG, "prove: no proving key loaded");
+    size_t n = (size_t)1 << ctx->log_n;
+    if (ctx->pk_len[Q_A] + 1 != ctx->m)
+        return set_err(ctx, G16_ERR_BAD_ARG, "prove: a_query has %zu points for %llu wires", ctx->pk_len[Q_A] + 1, (unsigned long long)ctx->m);
+    if (ctx->pk_len[Q_L] != ctx->m - ctx->ni)
+        return set_err(ctx, G16_ERR_BAD_ARG, "prove: l_query has %zu points for %llu witness wires", ctx->pk_len[Q_L],
+                       (unsigned long long)(ctx->m - ctx->ni));
+    if (ctx->pk_len[Q_H] > n) return set_err(ctx, G16_ERR_BAD_ARG, "prove: h_query longer than the domain");
+    return G16_OK;
+}
+
+struct PartialLayout {
+    G1XYZZ h, l, a, b1;
+    G2XYZZ b2;
+};
+
+// Runs witness map + the five (sharded) MSMs; leaves this rank's partial sums in ctx->d_partial.  Witness must be on the
+// device (ordered on main).  Work fans out from `main` to the side streams and joins back.
+static int prove_shard_streams(g16_ctx* ctx, int reduction) {
+    cudaStream_t main = ctx->main;
+    PartialLayout* part = (PartialLayout*)ctx->d_partial;
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
+    // z-only MSMs on the side streams: l (aux = z[ni..]), a / b_g1 / b_g2 (assignment = z[1..])   (prover.rs:70-74,89-117)
+    const int side_q[4] = {Q_L, Q_A, Q_B1, Q_B2};
+    for (int k = 0; k < 4; k++) {
+        cudaStream_t st = ctx->side[k];
+        int qi = side_q[k];
+        G16_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+        const Fr* sc = ctx->d_z + (qi == Q_L ? ctx->ni : 1) + ctx->sh_lo[qi];
+        size_t cnt = ctx->sh_hi[qi] - ctx->sh_lo[qi];
+        G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * qi], st));
+        G16_TRY(msm_run(ctx, &ctx->q[qi], &ctx->scratch[qi], sc, cnt, st));
+        void* dst = qi == Q_L ? (void*)&part->l : qi == Q_A ? (void*)&part->a : qi == Q_B1 ? (void*)&part->b1 : (void*)&part->b2;
+        size_t bytes = qi == Q_B2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
+        if (cnt && ctx->scratch[qi].result)
+            G16_CUDA(ctx, cudaMemcpyAsync(dst, ctx->scratch[qi].result, bytes, cudaMemcpyDeviceToDevice, st));
+        else
+            G16_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, st));
+        G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * qi], st));
+        G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], st));
+    }
+    // main: witness map, then the h MSM over h[lo..hi)  (prover.rs:63-66; the zip drops h[n-1], generator.rs:178)
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[0], main));
+    G16_TRY(witness_map_dev(ctx, reduction, main));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[1], main));
+    {
+        size_t cnt = ctx->sh_hi[Q_H] - ctx->sh_lo[Q_H];
+        G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * Q_H], main));
+        G16_TRY(msm_run(ctx, &ctx->q[Q_H], &ctx->scratch[Q_H], ctx->d_a + ctx->sh_lo[Q_H], cnt, main));
+        if (cnt && ctx->scratch[Q_H].result)
+            G16_CUDA(ctx, cudaMemcpyAsync(&part->h, ctx->scratch[Q_H].result, sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, main));
+        else
+            G16_CUDA(ctx, cudaMemsetAsync(&part->h, 0, sizeof(G1XYZZ), main));
+        G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * Q_H], main));
+    }
+    for (int k = 0; k < 4; k++) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[k], 0));
+    return G16_OK;
+}
+
+static void collect_timings(g16_ctx* ctx, bool with_asm) {
+    auto el = [&](int a, int b) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev_t[a], ctx->ev_t[b]) != cudaSuccess) {
+            cudaGetLastError();
+            ms = -1;
+        }
+        return ms;
+    };
+    ctx->tm.witness_map_ms = el(0, 1);
+    ctx->tm.msm_h_ms = el(2, 3);
+    ctx->tm.msm_l_ms = el(4, 5);
+    ctx->tm.msm_a_ms = el(6, 7);
+    ctx->tm.msm_b_g1_ms = el(8, 9);
+    ctx->tm.msm_b_g2_ms = el(10, 11);
+    ctx->tm.h2d_ms = el(14, 0);
+    if (with_asm) {
+        ctx->tm.assemble_ms = el(12, 13);
+        ctx->tm.total_ms = el(14, 13);
+    } else {
+        ctx->tm.assemble_ms = 0;
+        ctx->tm.total_ms = el(14, 12);
+    }
+}
+
+static int prove_full(g16_ctx* ctx, const uint64_t* z, const uint64_t* r, const uint64_t* s, int reduction, g16_proof* out) {
+    if (!r || !s || !out) return set_err(ctx, G16_ERR_BAD_ARG, "prove: null r/s/out");
+    G16_TRY(check_ready(ctx));
+    if (ctx->shard_count != 1) return set_err(ctx, G16_ERR_BAD_ARG, "prove: context holds shard %d/%d; use prove_shard + prove_combine", ctx->shard_rank, ctx->shard_count);
+    cudaStream_t main = ctx->main;
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[14], main));
+    if (z) G16_TRY(upload_witness(ctx, z, main));
+    else if (!ctx->witness_resident) return set_err(ctx, G16_ERR_BAD_ARG, "prove_resident: no witness uploaded");
+    // (r, s, pk)-only scalar multiplications overlap everything else
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
+    G16_CUDA(ctx, cudaStreamWaitEvent(ctx->side[4], ctx->ev_fork, 0));
+    G16_TRY(assemble_pre(ctx, r, s, ctx->side[4]));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[4], ctx->side[4]));
+    G16_TRY(prove_shard_streams(ctx, reduction));
+    G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[4], 0));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[12], main));
+    g16_proof tmp;
+    int rc = assemble_proof(ctx, ctx->d_partial, 1, r, s, &tmp, main);
+    if (rc != G16_OK) return rc;
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[13], main));
+    G16_CUDA(ctx, cudaStreamSynchronize(main));
+    collect_timings(ctx, true);
+    *out = tmp;
+    return G16_OK;
+}
+
+int g16_prove(g16_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64_t s[4], int reduction, g16_proof* out) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    if (!z) return set_err(ctx, G16_ERR_BAD_ARG, "prove: witness pointer is NULL");
+    Guard g(ctx);
+    return prove_full(ctx, z, r, s, reduction, out);
+}
+int g16_prove_resident(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], int reduction, g16_proof* out) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    return prove_full(ctx, nullptr, r, s, reduction, out);
+}
+
+int g16_prove_shard_dev(g16_ctx* ctx, int reduction) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_TRY(check_ready(ctx));
+    if (!ctx->witness_resident) return set_err(ctx, G16_ERR_BAD_ARG, "prove_shard_dev: no witness uploaded");
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[14], ctx->main));
+    G16_TRY(prove_shard_streams(ctx, reduction));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[12], ctx->main));
+    return G16_OK;
+}
+
+int g16_prove_shard(g16_ctx* ctx, const uint64_t* z, int reduction, g16_partial* out) {
+    if (!ctx || !out) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_TRY(check_ready(ctx));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[14], ctx->main));
+    G16_TRY(upload_witness(ctx, z, ctx->main));
+    G16_TRY(prove_shard_streams(ctx, reduction));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[12], ctx->main));
+    G16_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_partial, sizeof(g16_partial), cudaMemcpyDeviceToHost, ctx->main));
+    G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    collect_timings(ctx, false);
+    return G16_OK;
+}
+
+int g16_partial_dev(g16_ctx* ctx, void** dev_ptr, size_t* bytes) {
+    if (!ctx || !dev_ptr || !bytes) return G16_ERR_BAD_ARG;
+    *dev_ptr = ctx->d_partial;
+    *bytes = sizeof(g16_partial);
+    return G16_OK;
+}
+
+int g16_prove_combine_dev(g16_ctx* ctx, const void* dev_partials, int count, const uint64_t r[4], const uint64_t s[4],
+                          g16_proof* out) {
+    if (!ctx || !dev_partials || !r || !s || !out || count < 1) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "prove_combine: bad argument") : G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!ctx->have_pk) return set_err(ctx, G16_ERR_BAD_ARG, "prove_combine: no proving key loaded");
+    G16_TRY(assemble_pre(ctx, r, s, ctx->main));
+    return assemble_proof(ctx, dev_partials, count, r, s, out, ctx->main);
+}
+
+int g16_prove_combine(g16_ctx* ctx, const g16_partial* partials, int count, const uint64_t r[4], const uint64_t s[4],
+                      g16_proof* out) {
+    if (!ctx || !partials || count < 1) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "prove_combine: bad argument") : G16_ERR_BAD_ARG;
+    void* d = nullptr;
+    {
+        Guard g(ctx);
+        G16_CUDA(ctx, cudaMalloc(&d, sizeof(g16_partial) * (size_t)count));
+        G16_CUDA(ctx, cudaMemcpy(d, partials, sizeof(g16_partial) * (size_t)count, cudaMemcpyHostToDevice));
+    }
+    int rc = g16_prove_combine_dev(ctx, d, count, r, s, out);
+    cudaFree(d);
+    return rc;
+}
+
+int g16_get_timings(g16_ctx* ctx, g16_timings* out) {
+    if (!ctx || !out) return G16_ERR_BAD_ARG;
+    *out = ctx->tm;
+    return G16_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,401 @@
+// fp.cuh -- BN254 Fr / Fq Montgomery arithmetic on 8 x 32-bit limbs for sm_100a.
+//
+// Replaces the arithmetic the reference gets from ark-ff 0.4 `Fp<MontBackend<_,4>,4>` (used at
+// forks/groth16/src/r1cs_to_qap.rs:16-45,187,205-208 and prover.rs:63-65).  The in-memory form is
+// identical: 4 x u64 LE limbs of a*2^256 mod p == 8 x u32 LE limbs.
+//
+// Multiplication is a word-serial (CIOS) Montgomery product.  A 32x32 product occupies a 64-bit
+// lane, so partial products of the even limbs of an operand never overlap each other, nor do those of
+// the odd limbs: we keep two accumulators ("ev" aligned at limb 0, "od" aligned at limb 1) and every
+// row of the product is two straight carry chains of mad.lo.cc / madc.hi.cc that ptxas turns into
+// IMAD.WIDE.U32 with carry-in/out.  Each chain lives inside ONE asm statement, so we never rely on the
+// carry flag surviving between statements.
+//
+// The same source compiles for the host (gcc) with the chains emulated in C: tests/host_fp_test.cpp
+// runs exactly this control flow against the big-integer oracle without a GPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define G16_HD __host__ __device__ __forceinline__
+#define G16_D __device__ __forceinline__
+// big cold-path routines (full additions, doublings, inversions) are real calls: keeps ptxas time and code size sane
+#define G16_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define G16_HD inline
+#define G16_D inline
+#define G16_HD_NOINLINE inline
+#endif
+
+namespace g16 {
+
+struct limbs8 {
+    uint32_t v[8];
+};
+
+// ---------------------------------------------------------------------------------------------
+// carry-chain primitives.  acc is 8 limbs = four 64-bit lanes; (x0,x1,x2,x3) are the four 32-bit
+// multiplicands feeding those lanes.
+// ---------------------------------------------------------------------------------------------
+
+// acc = {x0,x1,x2,x3} * b   (no carries: lanes are disjoint)
+G16_HD void lanes_mul(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=&r"(acc[0]), "=&r"(acc[1]), "=&r"(acc[2]), "=&r"(acc[3]), "=&r"(acc[4]), "=&r"(acc[5]), "=&r"(acc[6]),
+          "=&r"(acc[7])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+#else
+    const uint32_t x[4] = {x0, x1, x2, x3};
+    for (int k = 0; k < 4; k++) {
+        uint64_t p = (uint64_t)x[k] * b;
+        acc[2 * k] = (uint32_t)p;
+        acc[2 * k + 1] = (uint32_t)(p >> 32);
+    }
+#endif
+}
+
+// acc += {x0,x1,x2,x3} * b as one carry chain; returns the carry out of limb 7 (0 or 1)
+G16_HD uint32_t lanes_mad(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+    uint32_t cy;
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "=r"(cy)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+#else
+    const uint32_t x[4] = {x0, x1, x2, x3};
+    uint64_t c = 0;
+    for (int k = 0; k < 4; k++) {
+        uint64_t p = (uint64_t)x[k] * b;
+        uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + c;
+        acc[2 * k] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)acc[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+        acc[2 * k + 1] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+    cy = (uint32_t)c;
+#endif
+    return cy;
+}
+
+// The per-row "fold + shift + multiply-add" step of the interleaved Montgomery product.
+//   e0  += sh[1]                      (stray limb of the accumulator being shifted out; carry -> next limb)
+//   sh[k] = sh[k+2] + lane product    (accumulator moves down 64 bits while the new row is added)
+//   sh[6],sh[7] = top lane product (+ carry)
+G16_HD void lanes_fold_shift_mad(uint32_t& e0, uint32_t* sh, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3,
+                                 uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %9, %13, %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, %13, %4;\n\t"
+        "madc.lo.cc.u32 %3, %10, %13, %5;\n\t"
+        "madc.hi.cc.u32 %4, %10, %13, %6;\n\t"
+        "madc.lo.cc.u32 %5, %11, %13, %7;\n\t"
+        "madc.hi.cc.u32 %6, %11, %13, %8;\n\t"
+        "madc.lo.cc.u32 %7, %12, %13, 0;\n\t"
+        "madc.hi.u32 %8, %12, %13, 0;"
+        : "+r"(e0), "+r"(sh[0]), "+r"(sh[1]), "+r"(sh[2]), "+r"(sh[3]), "+r"(sh[4]), "+r"(sh[5]), "+r"(sh[6]),
+          "+r"(sh[7])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+#else
+    const uint32_t x[4] = {x0, x1, x2, x3};
+    uint64_t t = (uint64_t)e0 + sh[1];
+    e0 = (uint32_t)t;
+    uint64_t c = t >> 32;
+    for (int k = 0; k < 4; k++) {
+        uint64_t p = (uint64_t)x[k] * b;
+        uint32_t add_lo = (k < 3) ? sh[2 * k + 2] : 0u;
+        uint32_t add_hi = (k < 3) ? sh[2 * k + 3] : 0u;
+        uint64_t lo = (uint64_t)add_lo + (uint32_t)p + c;
+        uint64_t hi = (uint64_t)add_hi + (uint32_t)(p >> 32) + (lo >> 32);
+        sh[2 * k] = (uint32_t)lo;
+        sh[2 * k + 1] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+#endif
+}
+
+// r = a + b (8 limbs), returns carry
+G16_HD uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t cy;
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=r"(cy)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+          "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t t = (uint64_t)a[i] + b[i] + c;
+        r[i] = (uint32_t)t;
+        c = t >> 32;
+    }
+    cy = (uint32_t)c;
+#endif
+    return cy;
+}
+
+// r = a - b (8 limbs), returns borrow (1 if a < b)
+G16_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t bw;
+#ifdef __CUDA_ARCH__
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=r"(bw)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+          "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    bw &= 1u;
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t t = (uint64_t)a[i] - b[i] - c;
+        r[i] = (uint32_t)t;
+        c = (t >> 32) & 1u;
+    }
+    bw = (uint32_t)c;
+#endif
+    return bw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Field parameters.  P = modulus limbs, INV = -p^-1 mod 2^32, R1 = 2^256 mod p (Montgomery one),
+// R2 = 2^512 mod p.  Values: SURVEY appendix, re-derived by oracle/pyref.py in tests/test_constants.py.
+// ---------------------------------------------------------------------------------------------
+struct FrParams {
+    static G16_HD constexpr uint32_t P(int i) {
+        constexpr uint32_t t[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return t[i];
+    }
+    static constexpr uint32_t INV = 0xefffffffu;
+    static G16_HD constexpr uint32_t R1(int i) {
+        constexpr uint32_t t[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return t[i];
+    }
+    static G16_HD constexpr uint32_t R2(int i) {
+        constexpr uint32_t t[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return t[i];
+    }
+};
+struct FqParams {
+    static G16_HD constexpr uint32_t P(int i) {
+        constexpr uint32_t t[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return t[i];
+    }
+    static constexpr uint32_t INV = 0xe4866389u;
+    static G16_HD constexpr uint32_t R1(int i) {
+        constexpr uint32_t t[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return t[i];
+    }
+    static G16_HD constexpr uint32_t R2(int i) {
+        constexpr uint32_t t[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return t[i];
+    }
+};
+
+template <class PR>
+struct alignas(16) Fp {
+    uint32_t v[8];  // Montgomery form, fully reduced: 0 <= v < p
+
+    static G16_HD void load_p(uint32_t* p) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) p[i] = PR::P(i);
+    }
+    static G16_HD Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = 0;
+        return r;
+    }
+    static G16_HD Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = PR::R1(i);
+        return r;
+    }
+    static G16_HD Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = PR::R2(i);
+        return r;
+    }
+    G16_HD bool is_zero() const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o |= v[i];
+        return o == 0;
+    }
+    G16_HD bool operator==(const Fp& b) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i];
+        return o == 0;
+    }
+    G16_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+
+    // conditional subtract of p: x in [0, 2p) (+ optional carry bit) -> [0, p)
+    static G16_HD void reduce_once(uint32_t* x, uint32_t carry) {
+        uint32_t t[8], p[8];
+        load_p(p);
+        uint32_t bw = sub8(t, x, p);
+        // keep t when there was no borrow, or when the 257-bit value had its top bit set
+        bool take = (bw == 0) | (carry != 0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = take ? t[i] : x[i];
+    }
+
+    friend G16_HD Fp operator+(const Fp& a, const Fp& b) {
+        Fp r;
+        uint32_t cy = add8(r.v, a.v, b.v);  // p < 2^254 so cy is always 0; kept for generality
+        reduce_once(r.v, cy);
+        return r;
+    }
+    friend G16_HD Fp operator-(const Fp& a, const Fp& b) {
+        Fp r;
+        uint32_t bw = sub8(r.v, a.v, b.v);
+        uint32_t t[8], p[8];
+        load_p(p);
+        add8(t, r.v, p);
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = bw ? t[i] : r.v[i];
+        return r;
+    }
+    G16_HD Fp neg() const {
+        Fp r;
+        uint32_t p[8];
+        load_p(p);
+        sub8(r.v, p, v);
+        bool z = is_zero();
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = z ? 0u : r.v[i];
+        return r;
+    }
+    G16_HD Fp dbl() const { return *this + *this; }
+
+    // Montgomery product a*b*2^-256 mod p
+    friend G16_HD Fp operator*(const Fp& a, const Fp& b) {
+        uint32_t X[8], Y[8];  // the two accumulators; their even/odd roles alternate every row
+        uint32_t m, cy;
+        // row 0
+        lanes_mul(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);  // even-aligned
+        lanes_mul(Y, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);  // odd-aligned (limb k of Y sits at position k+1)
+        m = X[0] * PR::INV;
+        lanes_mad(Y, PR::P(1), PR::P(3), PR::P(5), PR::P(7), m);  // cannot carry out (total < 2^288)
+        cy = lanes_mad(X, PR::P(0), PR::P(2), PR::P(4), PR::P(6), m);
+        Y[7] += cy;
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            uint32_t* ev = (i & 1) ? Y : X;  // becomes the even-aligned accumulator after the 32-bit shift
+            uint32_t* od = (i & 1) ? X : Y;  // old even accumulator: limb 0 is zero, limb 1 is folded into ev[0]
+            lanes_fold_shift_mad(ev[0], od, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+            cy = lanes_mad(ev, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+            od[7] += cy;
+            m = ev[0] * PR::INV;
+            lanes_mad(od, PR::P(1), PR::P(3), PR::P(5), PR::P(7), m);
+            cy = lanes_mad(ev, PR::P(0), PR::P(2), PR::P(4), PR::P(6), m);
+            od[7] += cy;
+        }
+        // after row 7 the even accumulator is Y (i=7 odd -> ev=Y), odd is X; result = (ev >> 32) + od
+        Fp r;
+        uint32_t sh[8];
+#pragma unroll
+        for (int k = 0; k < 7; k++) sh[k] = Y[k + 1];
+        sh[7] = 0;
+        cy = add8(r.v, sh, X);
+        reduce_once(r.v, cy);
+        return r;
+    }
+    G16_HD Fp sqr() const { return (*this) * (*this); }
+
+    // to / from Montgomery form
+    G16_HD Fp to_mont() const { return (*this) * r2(); }
+    G16_HD Fp from_mont() const {
+        Fp o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.v[i] = (i == 0) ? 1u : 0u;
+        return (*this) * o;
+    }
+
+    // a^(p-2); exponent bits are compile-time constants of the field
+    G16_HD_NOINLINE Fp inverse() const {
+        uint32_t e[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) e[i] = PR::P(i);
+        e[0] -= 2u;  // both moduli have low limb >= 2, no borrow
+        Fp acc = one();
+        for (int i = 7; i >= 0; i--) {
+            for (int bit = 31; bit >= 0; bit--) {
+                acc = acc.sqr();
+                if ((e[i] >> bit) & 1u) acc = acc * (*this);
+            }
+        }
+        return acc;
+    }
+};
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+// ---------------------------------------------------------------------------------------------
+// Fq2 = Fq[u]/(u^2+1)   (ark-bn254 Fq2Config: NONRESIDUE = -1)
+// ---------------------------------------------------------------------------------------------
+struct Fq2 {
+    Fq c0, c1;
+    static G16_HD Fq2 zero() { return Fq2{Fq::zero(), Fq::zero()}; }
+    static G16_HD Fq2 one() { return Fq2{Fq::one(), Fq::zero()}; }
+    G16_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    G16_HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
+    G16_HD bool operator!=(const Fq2& b) const { return !(*this == b); }
+    friend G16_HD Fq2 operator+(const Fq2& a, const Fq2& b) { return Fq2{a.c0 + b.c0, a.c1 + b.c1}; }
+    friend G16_HD Fq2 operator-(const Fq2& a, const Fq2& b) { return Fq2{a.c0 - b.c0, a.c1 - b.c1}; }
+    G16_HD Fq2 neg() const { return Fq2{c0.neg(), c1.neg()}; }
+    G16_HD Fq2 dbl() const { return Fq2{c0.dbl(), c1.dbl()}; }
+    // Karatsuba: 3 Fq multiplications
+    friend G16_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
+        Fq v0 = a.c0 * b.c0;
+        Fq v1 = a.c1 * b.c1;
+        Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
+        return Fq2{v0 - v1, s - v0 - v1};
+    }
+    // complex squaring: 2 Fq multiplications
+    G16_HD Fq2 sqr() const {
+        Fq t = c0 * c1;
+        return Fq2{(c0 + c1) * (c0 - c1), t.dbl()};
+    }
+    G16_HD_NOINLINE Fq2 inverse() const {
+        Fq n = (c0.sqr() + c1.sqr()).inverse();
+        return Fq2{c0 * n, (c1 * n).neg()};
+    }
+};
+
+}  // namespace g16

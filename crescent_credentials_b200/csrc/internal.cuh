@@ -1,0 +1,190 @@
+// internal.cuh -- context object and cross-translation-unit declarations of libg16b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/g16_b200.h"
+#include "ec.cuh"
+
+namespace g16 {
+
+constexpr int kSideStreams = 5;
+constexpr int kMsmSlots = 8;
+constexpr int kNumSMs = 148;  // B200
+
+// ---- NTT domain tables (one per log_n, built lazily on the device) ----------------------------------------------
+struct NttTables {
+    unsigned log_n = 0;
+    Fr* tw = nullptr;         // omega^k, k < n/2
+    Fr* tw_inv = nullptr;     // omega^-k, k < n/2
+    Fr* coset = nullptr;      // g^i, i < n                    (forward coset pre-scale)
+    Fr* coset_inv = nullptr;  // g^-i / n, i < n               (inverse coset post-scale)
+    Fr n_inv;                 // 1/n (host copy, Montgomery)
+    Fr zinv;                  // 1/(g^n - 1)
+    bool zinv_ok = false;
+    Fr* coset_scaled = nullptr;  // g^i / n                    (iNTT's 1/n folded into the following coset NTT)
+    Fr* odd_scaled = nullptr;    // omega_2n^i / n, i < n      (CircomReduction coset: qap.rs:63-72, same folding)
+};
+
+// ---- MSM engine state for one set of bases -------------------------------------------------------------------------
+struct MsmBases {
+    int group = 0;          // 1 = G1 (64 B points), 2 = G2 (128 B points)
+    size_t n = 0;           // number of (logical) points
+    int c = 0;              // window bits
+    int windows = 0;        // number of signed windows
+    bool precomp = false;   // bases hold windows * n points: 2^(c*w) * P_i at [w*n + i]
+    void* pts = nullptr;    // device: Affine<Fq> or Affine<Fq2>
+    bool owns_pts = true;
+    uint8_t* skip = nullptr;  // device: 1 if point i is infinity (b-queries hold many)
+};
+
+struct MsmScratch {
+    size_t cap_items = 0;    // capacity in (window,point) pairs
+    size_t cap_buckets = 0;  // capacity in buckets (sets * nb)
+    uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
+    uint32_t* hist = nullptr;       // radix histograms
+    size_t hist_cap = 0;
+    uint32_t* bucket_start = nullptr;  // sets*(nb+1)
+    uint32_t* task_off = nullptr;      // per bucket: first task id (exclusive scan of tasks per bucket), +1
+    uint32_t* task_tmp = nullptr;      // scan scratch
+    uint32_t* tasks = nullptr;         // sorted task ids
+    uint32_t* len_hist = nullptr;      // histogram of task lengths
+    void* partial = nullptr;           // XYZZ per task
+    size_t cap_tasks = 0;
+    void* bucket_sum = nullptr;        // XYZZ per bucket
+    void* chunk_sum = nullptr;         // XYZZ per chunk
+    void* block_sum = nullptr;         // XYZZ per reduce block
+    void* result = nullptr;            // XYZZ final (device)
+    uint32_t* counters = nullptr;      // misc device counters
+    size_t point_bytes = 0;
+};
+
+struct CsrDev {
+    uint64_t* row_ptr = nullptr;
+    uint32_t* col = nullptr;
+    Fr* val = nullptr;
+    size_t nnz = 0;
+};
+
+}  // namespace g16
+
+struct g16_ctx {
+    int device = 0;
+    cudaStream_t main = nullptr;
+    bool own_main = false;
+    cudaStream_t side[g16::kSideStreams] = {};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[g16::kSideStreams] = {};
+    cudaEvent_t ev_t[16] = {};
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+
+    std::map<unsigned, g16::NttTables> ntt;
+
+    // R1CS
+    bool have_r1cs = false;
+    uint64_t nc = 0, ni = 0, m = 0;
+    unsigned log_n = 0;
+    g16::CsrDev mat[3];
+    g16::Fr *d_z = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;  // witness + three n-vectors
+    uint64_t* h_pinned = nullptr;                                           // pinned staging for z
+    size_t h_pinned_bytes = 0;
+    bool witness_resident = false;
+
+    // proving key
+    bool have_pk = false;
+    int shard_rank = 0, shard_count = 1;
+    size_t pk_len[5] = {};  // full lengths of h, l, a, b_g1, b_g2 MSM ranges
+    size_t sh_lo[5] = {}, sh_hi[5] = {};
+    g16::MsmBases q[5];     // h, l, a(1..), b_g1(1..), b_g2(1..)
+    g16::MsmScratch scratch[5];
+    g16::G1Affine alpha_g1, beta_g1, delta_g1, a0, b1_0;  // host copies (Montgomery)
+    g16::G2Affine beta_g2, delta_g2, b2_0;
+    void* d_partial = nullptr;  // g16_partial on the device
+    void* d_small = nullptr;    // small device scratch for assembly
+    g16_timings tm = {};
+
+    // generic MSM slots
+    g16::MsmBases slot[g16::kMsmSlots];
+    g16::MsmScratch slot_scratch[g16::kMsmSlots];
+};
+
+namespace g16 {
+
+// error helpers -----------------------------------------------------------------------------------------------------
+int set_err(g16_ctx* ctx, int code, const char* fmt, ...);
+#define G16_CUDA(ctx, expr)                                                                            \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return g16::set_err(ctx, _e == cudaErrorMemoryAllocation ? G16_ERR_OOM : G16_ERR_CUDA,     \
+                                "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define G16_TRY(expr)                 \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != G16_OK) return _rc; \
+    } while (0)
+#define G16_LAUNCH(ctx, kern, grid, block, smem, stream, ...)                       \
+    do {                                                                            \
+        kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                   \
+        (ctx)->launches++;                                                          \
+        G16_CUDA(ctx, cudaPeekAtLastError());                                       \
+    } while (0)
+
+template <class T>
+int dev_alloc(g16_ctx* ctx, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return G16_OK;
+    G16_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
+    return G16_OK;
+}
+inline void dev_free(void* p) {
+    if (p) cudaFree(p);
+}
+
+// field_ops.cu ------------------------------------------------------------------------------------------------------
+int field_op_dev(g16_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n, cudaStream_t st);
+int bench_int_pipe(g16_ctx* ctx, int which, double* gops);
+int convert_mont_dev(g16_ctx* ctx, int field /*FR|FQ*/, void* data, size_t n_elems, bool to_mont, cudaStream_t st);
+
+// ntt.cu --------------------------------------------------------------------------------------------------------------
+int ntt_get_tables(g16_ctx* ctx, unsigned log_n, NttTables** out);
+// core transforms on device data (no bit reversal):  dif: natural -> bit-reversed;  dit: bit-reversed -> natural.
+// pre (dif) / post (dit) are optional element-wise scale tables indexed by the natural index; post_scalar (dit) is an
+// optional uniform Montgomery factor.
+int ntt_dif(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* pre, cudaStream_t st);
+int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* post, const Fr* post_scalar,
+            cudaStream_t st);
+int bitrev_permute(g16_ctx* ctx, Fr* data, unsigned log_n, cudaStream_t st);
+int ntt_api(g16_ctx* ctx, Fr* data_dev, unsigned log_n, int inverse, int coset, cudaStream_t st);
+
+// witness.cu ------------------------------------------------------------------------------------------------------------
+int witness_map_dev(g16_ctx* ctx, int reduction, cudaStream_t st);  // z in ctx->d_z; h left in ctx->d_a (natural order)
+int r1cs_eval_dev(g16_ctx* ctx, Fr* az, Fr* bz, Fr* cz, bool bitrev, cudaStream_t st);
+
+// msm.cu ----------------------------------------------------------------------------------------------------------------
+int msm_pick_window(size_t n, int group, bool precomp);
+int msm_set_bases(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, int group, const void* pts_dev, size_t n, int c,
+                  bool precomp, cudaStream_t st);
+void msm_free(MsmBases* mb, MsmScratch* sc);
+// runs Pippenger over the first n bases with device scalars (Montgomery Fr); leaves the XYZZ result in sc->result
+int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st);
+int fixed_base_dev(g16_ctx* ctx, int group, const Fr* scalars_dev, size_t n, void* out_pts_dev, cudaStream_t st);
+
+// assemble.cu -----------------------------------------------------------------------------------------------------------
+int assemble_pre(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, cudaStream_t st);
+G1Affine g1_generator();
+G2Affine g2_generator();
+int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, const uint64_t* r, const uint64_t* s,
+                   g16_proof* out, cudaStream_t st);
+int xyzz_to_affine_host(g16_ctx* ctx, int group, const void* xyzz_dev, uint64_t* out, int* out_inf, cudaStream_t st);
+
+}  // namespace g16

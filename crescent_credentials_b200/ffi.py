@@ -1,0 +1,352 @@
+"""ctypes binding of libg16b200.so (include/g16_b200.h).  No compute happens in Python and there is no fallback:
+if the CUDA library is missing or no device is visible, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libg16b200.so")
+
+G16_OK = 0
+ERR_DEGREE_TOO_LARGE, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_VANISHING_ZERO = 1, 2, 3, 4, 5, 6
+REDUCTION_LIBSNARK, REDUCTION_CIRCOM = 0, 1
+ENC_MONTGOMERY, ENC_CANONICAL = 0, 1
+FIELD_FR, FIELD_FQ, FIELD_FQ2 = 0, 1, 2
+OP_MUL, OP_ADD, OP_SUB, OP_NEG, OP_INV, OP_TO_MONT, OP_FROM_MONT, OP_SQR = range(8)
+PARTIAL_U64 = 4 * 16 + 32
+
+# every symbol include/g16_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "g16_device_count", "g16_ctx_create", "g16_ctx_destroy", "g16_last_error", "g16_version", "g16_ctx_load_pk",
+    "g16_ctx_load_r1cs", "g16_prove", "g16_upload_witness", "g16_prove_resident", "g16_prove_shard",
+    "g16_prove_combine", "g16_partial_dev", "g16_prove_shard_dev", "g16_prove_combine_dev", "g16_witness_map",
+    "g16_domain_size", "g16_get_timings", "g16_msm_g1", "g16_msm_g2", "g16_msm_set_bases", "g16_msm_set_bases_dev",
+    "g16_msm_run_dev", "g16_ntt", "g16_ntt_dev", "g16_field_op", "g16_fixed_base_g1", "g16_fixed_base_g2",
+    "g16_fixed_base_g1_dev", "g16_fixed_base_g2_dev", "g16_r1cs_eval", "g16_dev_alloc", "g16_dev_free",
+    "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count",
+]
+
+_u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
+
+
+class PkView(C.Structure):
+    _fields_ = [
+        ("a_query", _u64p), ("a_len", C.c_size_t),
+        ("b_g1_query", _u64p), ("b_g1_len", C.c_size_t),
+        ("b_g2_query", _u64p), ("b_g2_len", C.c_size_t),
+        ("h_query", _u64p), ("h_len", C.c_size_t),
+        ("l_query", _u64p), ("l_len", C.c_size_t),
+        ("alpha_g1", _u64p), ("beta_g1", _u64p), ("delta_g1", _u64p), ("beta_g2", _u64p), ("delta_g2", _u64p),
+        ("encoding", C.c_int),
+    ]
+
+
+class R1csView(C.Structure):
+    _fields_ = [
+        ("num_constraints", C.c_uint64), ("num_instance", C.c_uint64), ("num_wires", C.c_uint64),
+        ("row_ptr", _u64p * 3), ("col", _u32p * 3), ("val", _u64p * 3), ("encoding", C.c_int),
+    ]
+
+
+class ProofOut(C.Structure):
+    _fields_ = [("a", C.c_uint64 * 8), ("b", C.c_uint64 * 16), ("c", C.c_uint64 * 8),
+                ("a_inf", C.c_int32), ("b_inf", C.c_int32), ("c_inf", C.c_int32), ("_pad", C.c_int32)]
+
+
+class Partial(C.Structure):
+    _fields_ = [("w", C.c_uint64 * PARTIAL_U64)]
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "witness_map_ms", "msm_h_ms", "msm_l_ms", "msm_a_ms",
+                                         "msm_b_g1_ms", "msm_b_g2_ms", "assemble_ms", "total_ms")]
+
+    def as_dict(self):
+        return {n: float(getattr(self, n)) for n, _ in self._fields_}
+
+
+class G16Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libg16b200 error {code}: {msg}")
+        self.code = code
+
+
+class PolynomialDegreeTooLarge(G16Error):
+    """SynthesisError::PolynomialDegreeTooLarge (forks/groth16/src/r1cs_to_qap.rs:156-157)."""
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.g16_last_error.restype = C.c_char_p
+    lib.g16_last_error.argtypes = [C.c_void_p]
+    lib.g16_version.restype = C.c_char_p
+    lib.g16_launch_count.restype = C.c_uint64
+    lib.g16_launch_count.argtypes = [C.c_void_p]
+    lib.g16_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    lib.g16_ctx_destroy.argtypes = [C.c_void_p]
+    lib.g16_ctx_destroy.restype = None
+    lib.g16_ctx_load_pk.argtypes = [C.c_void_p, C.POINTER(PkView), C.c_int, C.c_int, C.c_int]
+    lib.g16_ctx_load_r1cs.argtypes = [C.c_void_p, C.POINTER(R1csView)]
+    lib.g16_prove.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ProofOut)]
+    lib.g16_upload_witness.argtypes = [C.c_void_p, C.c_void_p]
+    lib.g16_prove_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ProofOut)]
+    lib.g16_prove_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Partial)]
+    lib.g16_prove_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
+    lib.g16_partial_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.g16_prove_shard_dev.argtypes = [C.c_void_p, C.c_int]
+    lib.g16_prove_combine_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
+    lib.g16_witness_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.g16_domain_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+    lib.g16_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
+    lib.g16_msm_g1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]
+    lib.g16_msm_g2.argtypes = lib.g16_msm_g1.argtypes
+    lib.g16_msm_set_bases.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    lib.g16_msm_set_bases_dev.argtypes = lib.g16_msm_set_bases.argtypes
+    lib.g16_msm_run_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]
+    lib.g16_ntt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int]
+    lib.g16_ntt_dev.argtypes = lib.g16_ntt.argtypes
+    lib.g16_field_op.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    for n in ("g16_fixed_base_g1", "g16_fixed_base_g2", "g16_fixed_base_g1_dev", "g16_fixed_base_g2_dev"):
+        getattr(lib, n).argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.g16_r1cs_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.g16_dev_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.g16_dev_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.g16_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.g16_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.g16_sync.argtypes = [C.c_void_p]
+    lib.g16_bench_int_pipe.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """numpy array / int address / None -> void* (arrays must be C-contiguous)."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """Owns one g16_ctx (one CUDA device).  `stream` is an optional raw cudaStream_t (e.g. torch's current stream)."""
+
+    def __init__(self, device: int = 0, stream: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.g16_ctx_create(C.byref(h), device, C.c_void_p(stream) if stream else None)
+        if rc != G16_OK:
+            raise G16Error(rc, self.lib.g16_last_error(None).decode())
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.g16_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != G16_OK:
+            msg = self.lib.g16_last_error(self.h).decode()
+            if rc == ERR_DEGREE_TOO_LARGE:
+                raise PolynomialDegreeTooLarge(rc, msg)
+            raise G16Error(rc, msg)
+
+    # -- building blocks -------------------------------------------------------------------------------------
+    def field_op(self, field: int, op: int, a: np.ndarray, b: Optional[np.ndarray] = None) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        w = 8 if field == FIELD_FQ2 else 4
+        n = a.size // w
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.uint64)
+        self.check(self.lib.g16_field_op(self.h, field, op, _ptr(a), _ptr(b), _ptr(out), n))
+        return out
+
+    def ntt(self, data: np.ndarray, inverse: bool = False, coset: bool = False) -> np.ndarray:
+        d = np.array(data, dtype=np.uint64, order="C", copy=True).reshape(-1, 4)
+        n = d.shape[0]
+        log_n = max(n.bit_length() - 1, 0)
+        if n == 0 or (1 << log_n) != n:
+            raise G16Error(ERR_BAD_ARG, "NTT size must be a power of two")
+        self.check(self.lib.g16_ntt(self.h, _ptr(d), log_n, int(inverse), int(coset)))
+        return d
+
+    def msm(self, group: int, points: np.ndarray, scalars: np.ndarray):
+        pw = 8 if group == 1 else 16
+        points = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, pw)
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        n = min(points.shape[0], scalars.shape[0])  # msm_bigint zips (prover.rs:66)
+        out = np.zeros(pw, dtype=np.uint64)
+        inf = C.c_int(0)
+        fn = self.lib.g16_msm_g1 if group == 1 else self.lib.g16_msm_g2
+        self.check(fn(self.h, _ptr(points), _ptr(scalars), n, _ptr(out), C.byref(inf)))
+        return out, bool(inf.value)
+
+    def fixed_base(self, group: int, scalars: np.ndarray) -> np.ndarray:
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        pw = 8 if group == 1 else 16
+        out = np.zeros((scalars.shape[0], pw), dtype=np.uint64)
+        fn = self.lib.g16_fixed_base_g1 if group == 1 else self.lib.g16_fixed_base_g2
+        self.check(fn(self.h, _ptr(scalars), scalars.shape[0], _ptr(out)))
+        return out
+
+    def bench_int_pipe(self, which: int) -> float:
+        v = C.c_double(0)
+        self.check(self.lib.g16_bench_int_pipe(self.h, which, C.byref(v)))
+        return v.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.g16_launch_count(self.h))
+
+    def sync(self):
+        self.check(self.lib.g16_sync(self.h))
+
+    # -- device memory ----------------------------------------------------------------------------------------
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self.check(self.lib.g16_dev_alloc(self.h, nbytes, C.byref(p)))
+        return int(p.value)
+
+    def dev_free(self, p: int):
+        self.check(self.lib.g16_dev_free(self.h, C.c_void_p(p)))
+
+    def dev_upload(self, p: int, a: np.ndarray):
+        a = np.ascontiguousarray(a)
+        self.check(self.lib.g16_dev_upload(self.h, C.c_void_p(p), _ptr(a), a.nbytes))
+
+    def dev_download(self, p: int, out: np.ndarray):
+        self.check(self.lib.g16_dev_download(self.h, _ptr(out), C.c_void_p(p), out.nbytes))
+        return out
+
+    # -- the hot path -------------------------------------------------------------------------------------------
+    def load_r1cs(self, nc: int, ni: int, m: int, row_ptr, col, val, encoding=ENC_MONTGOMERY):
+        v = R1csView()
+        v.num_constraints, v.num_instance, v.num_wires, v.encoding = nc, ni, m, encoding
+        keep = []
+        for k in range(3):
+            rp = np.ascontiguousarray(row_ptr[k], dtype=np.uint64)
+            cc = np.ascontiguousarray(col[k], dtype=np.uint32)
+            vv = np.ascontiguousarray(val[k], dtype=np.uint64)
+            keep += [rp, cc, vv]
+            v.row_ptr[k] = C.cast(rp.ctypes.data, _u64p)
+            v.col[k] = C.cast(cc.ctypes.data, _u32p)
+            v.val[k] = C.cast(vv.ctypes.data, _u64p)
+        self.check(self.lib.g16_ctx_load_r1cs(self.h, C.byref(v)))
+
+    def load_pk(self, arrays: dict, encoding=ENC_MONTGOMERY, shard_rank=0, shard_count=1, precompute=False):
+        """arrays: a_query, b_g1_query, b_g2_query, h_query, l_query (n x 8 / n x 16 uint64) and the single points
+        alpha_g1, beta_g1, delta_g1 (8), beta_g2, delta_g2 (16)."""
+        v = PkView()
+        keep = {}
+        for name in ("a_query", "b_g1_query", "b_g2_query", "h_query", "l_query"):
+            w = 16 if name == "b_g2_query" else 8
+            a = np.ascontiguousarray(arrays[name], dtype=np.uint64).reshape(-1, w)
+            keep[name] = a
+            setattr(v, name, C.cast(a.ctypes.data, _u64p))
+            setattr(v, name.replace("_query", "_len"), a.shape[0])
+        for name in ("alpha_g1", "beta_g1", "delta_g1", "beta_g2", "delta_g2"):
+            a = np.ascontiguousarray(arrays[name], dtype=np.uint64).reshape(-1)
+            keep[name] = a
+            setattr(v, name, C.cast(a.ctypes.data, _u64p))
+        v.encoding = encoding
+        self.check(self.lib.g16_ctx_load_pk(self.h, C.byref(v), shard_rank, shard_count, int(precompute)))
+
+    def domain_size(self) -> int:
+        n = C.c_size_t(0)
+        self.check(self.lib.g16_domain_size(self.h, C.byref(n)))
+        return int(n.value)
+
+    def witness_map(self, z: np.ndarray, reduction=REDUCTION_LIBSNARK) -> np.ndarray:
+        z = np.ascontiguousarray(z, dtype=np.uint64)
+        n = self.domain_size()
+        h = np.empty((n, 4), dtype=np.uint64)
+        got = C.c_size_t(0)
+        self.check(self.lib.g16_witness_map(self.h, _ptr(z), reduction, _ptr(h), n, C.byref(got)))
+        return h
+
+    def r1cs_eval(self, z: np.ndarray, nc: int):
+        z = np.ascontiguousarray(z, dtype=np.uint64)
+        out = [np.zeros((nc, 4), dtype=np.uint64) for _ in range(3)]
+        self.check(self.lib.g16_r1cs_eval(self.h, _ptr(z), _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        return out
+
+    def prove(self, z, r: np.ndarray, s: np.ndarray, reduction=REDUCTION_LIBSNARK) -> ProofOut:
+        """z: numpy (m x 4 uint64) or a raw host address (e.g. pinned memory) of m Montgomery elements."""
+        if isinstance(z, np.ndarray):
+            z = np.ascontiguousarray(z, dtype=np.uint64)
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        out = ProofOut()
+        self.check(self.lib.g16_prove(self.h, _ptr(z), _ptr(r), _ptr(s), reduction, C.byref(out)))
+        return out
+
+    def upload_witness(self, z):
+        if isinstance(z, np.ndarray):
+            z = np.ascontiguousarray(z, dtype=np.uint64)
+        self.check(self.lib.g16_upload_witness(self.h, _ptr(z)))
+
+    def prove_resident(self, r, s, reduction=REDUCTION_LIBSNARK) -> ProofOut:
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        out = ProofOut()
+        self.check(self.lib.g16_prove_resident(self.h, _ptr(r), _ptr(s), reduction, C.byref(out)))
+        return out
+
+    def prove_shard(self, z, reduction=REDUCTION_LIBSNARK) -> np.ndarray:
+        if isinstance(z, np.ndarray):
+            z = np.ascontiguousarray(z, dtype=np.uint64)
+        p = Partial()
+        self.check(self.lib.g16_prove_shard(self.h, _ptr(z), reduction, C.byref(p)))
+        return np.frombuffer(bytes(p), dtype=np.uint64).copy()
+
+    def prove_shard_dev(self, reduction=REDUCTION_LIBSNARK):
+        self.check(self.lib.g16_prove_shard_dev(self.h, reduction))
+
+    def partial_dev(self):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        self.check(self.lib.g16_partial_dev(self.h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def prove_combine(self, partials: np.ndarray, r, s) -> ProofOut:
+        partials = np.ascontiguousarray(partials, dtype=np.uint64).reshape(-1, PARTIAL_U64)
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        out = ProofOut()
+        self.check(self.lib.g16_prove_combine(self.h, _ptr(partials), partials.shape[0], _ptr(r), _ptr(s), C.byref(out)))
+        return out
+
+    def prove_combine_dev(self, dev_partials: int, count: int, r, s) -> ProofOut:
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        out = ProofOut()
+        self.check(self.lib.g16_prove_combine_dev(self.h, C.c_void_p(dev_partials), count, _ptr(r), _ptr(s), C.byref(out)))
+        return out
+
+    def timings(self) -> dict:
+        t = Timings()
+        self.check(self.lib.g16_get_timings(self.h, C.byref(t)))
+        return t.as_dict()

@@ -1,0 +1,204 @@
+/*
+ * g16_b200.h -- C ABI of libg16b200.so: a B200 (sm_100a) Groth16 prover for BN254 that drops in for the hot
+ * path of microsoft/crescent-credentials' `prove` step.
+ *
+ * Reference interface replaced (paths relative to the reference tree):
+ *   forks/groth16/src/prover.rs:26-34     Groth16::create_proof_with_reduction_and_matrices  -> g16_prove
+ *   forks/groth16/src/prover.rs:54-136    create_proof_with_assignment (5 MSMs + assembly)   -> g16_prove (second half),
+ *                                                                                               g16_prove_shard / g16_prove_combine
+ *   forks/groth16/src/r1cs_to_qap.rs:150-213  LibsnarkReduction::witness_map_from_matrices   -> g16_witness_map(reduction=0)
+ *   forks/circom-compat/src/circom/qap.rs:25-90  CircomReduction::witness_map_from_matrices  -> g16_witness_map(reduction=1)
+ *   ark-ec VariableBaseMSM::msm_bigint call sites prover.rs:66,74,266                         -> g16_msm_g1 / g16_msm_g2
+ *   ark-poly EvaluationDomain::{fft,ifft}_in_place (+ coset) call sites r1cs_to_qap.rs:179-210 -> g16_ntt
+ *   ark-ff Fp mul/add/sub/inverse (K1 parity hook)                                            -> g16_field_op
+ *   forks/groth16/src/generator.rs:133-194 FixedBase::msm (key minting, "next" row f-2)       -> g16_fixed_base_g1 / _g2
+ *
+ * Data layout at the boundary (all host pointers unless a function says "dev"):
+ *   Fr / Fq element : 4 x uint64 little-endian limbs in Montgomery form (R = 2^256) -- byte-identical to arkworks'
+ *                     in-memory `Fp<MontBackend<_,4>,4>` (BigInt<4>) and to 8 x uint32 limbs.
+ *   G1 affine point : x || y, 8 x uint64.  Infinity is (0, 0) (arkworks keeps a separate bool: the shim repacks).
+ *   G2 affine point : x.c0 || x.c1 || y.c0 || y.c1, 16 x uint64.  Infinity is all-zero.
+ *   CSR matrix      : row_ptr uint64[nc+1], col uint32[nnz], val 4 x uint64[nnz] (Montgomery) -- the flattening of
+ *                     ark-relations ConstraintMatrices {a,b,c}: Vec<Vec<(Fr, usize)>>.
+ * All functions return 0 on success or a G16_ERR_* code; no proof bytes are written on error.  There is no CPU fallback:
+ * without a CUDA device every compute entry point fails with G16_ERR_NO_DEVICE.
+ * Thread safety: any thread may call; calls on one context are serialised by an internal mutex.
+ */
+#ifndef G16_B200_H
+#define G16_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G16_OK 0
+#define G16_ERR_DEGREE_TOO_LARGE 1 /* SynthesisError::PolynomialDegreeTooLarge (r1cs_to_qap.rs:156-157) */
+#define G16_ERR_BAD_ARG 2          /* size mismatch / null pointer / not loaded */
+#define G16_ERR_CUDA 3
+#define G16_ERR_OOM 4
+#define G16_ERR_NO_DEVICE 5
+#define G16_ERR_VANISHING_ZERO 6 /* the reference's `.inverse().unwrap()` panic at r1cs_to_qap.rs:201-204 */
+
+#define G16_REDUCTION_LIBSNARK 0
+#define G16_REDUCTION_CIRCOM 1
+
+#define G16_ENC_MONTGOMERY 0 /* arkworks in-memory limbs */
+#define G16_ENC_CANONICAL 1  /* arkworks serialised (little-endian canonical integers, flag bits already cleared) */
+
+/* field ids / ops for g16_field_op */
+#define G16_FIELD_FR 0
+#define G16_FIELD_FQ 1
+#define G16_FIELD_FQ2 2
+#define G16_OP_MUL 0
+#define G16_OP_ADD 1
+#define G16_OP_SUB 2
+#define G16_OP_NEG 3
+#define G16_OP_INV 4
+#define G16_OP_TO_MONT 5
+#define G16_OP_FROM_MONT 6
+#define G16_OP_SQR 7
+
+typedef struct g16_ctx g16_ctx;
+
+/* Proving-key view: forks/groth16/src/data_structures.rs:101-118 (ProvingKey) + :31-44 (the vk fields the prover reads). */
+typedef struct g16_pk_view {
+    const uint64_t* a_query;    size_t a_len;    /* G1, m points (query[0] is the constant-1 wire) */
+    const uint64_t* b_g1_query; size_t b_g1_len; /* G1, m points */
+    const uint64_t* b_g2_query; size_t b_g2_len; /* G2, m points */
+    const uint64_t* h_query;    size_t h_len;    /* G1, n-1 points */
+    const uint64_t* l_query;    size_t l_len;    /* G1, m - num_instance points */
+    const uint64_t* alpha_g1;                    /* vk.alpha_g1 */
+    const uint64_t* beta_g1;
+    const uint64_t* delta_g1;
+    const uint64_t* beta_g2;                     /* vk.beta_g2 */
+    const uint64_t* delta_g2;                    /* vk.delta_g2 */
+    int encoding;                                /* G16_ENC_* of every coordinate above */
+} g16_pk_view;
+
+/* R1CS view: the three ConstraintMatrices flattened to CSR. */
+typedef struct g16_r1cs_view {
+    uint64_t num_constraints;
+    uint64_t num_instance; /* l, including the constant 1 */
+    uint64_t num_wires;    /* m = instance + witness */
+    const uint64_t* row_ptr[3];
+    const uint32_t* col[3];
+    const uint64_t* val[3];
+    int encoding; /* G16_ENC_* of val */
+} g16_r1cs_view;
+
+/* Proof{a, b, c} (data_structures.rs:7-14), affine, Montgomery limbs; *_inf != 0 marks the point at infinity. */
+typedef struct g16_proof {
+    uint64_t a[8];
+    uint64_t b[16];
+    uint64_t c[8];
+    int32_t a_inf, b_inf, c_inf;
+    int32_t _pad;
+} g16_proof;
+
+/* Per-rank partial results of the five sharded MSMs (XYZZ, Montgomery): h, l, a, b_g1 (16 x u64 each), b_g2 (32 x u64). */
+#define G16_PARTIAL_U64 (4 * 16 + 32)
+typedef struct g16_partial {
+    uint64_t w[G16_PARTIAL_U64];
+} g16_partial;
+
+/* Device-side stage timings of the last g16_prove / g16_prove_shard on this context, milliseconds (CUDA events on the
+ * context's streams).  Stage names follow the reference's start_timer! labels (prover.rs:35-36,62,93,103,115,123). */
+typedef struct g16_timings {
+    float h2d_ms;         /* witness upload */
+    float witness_map_ms; /* "R1CS to QAP witness map" */
+    float msm_h_ms, msm_l_ms, msm_a_ms, msm_b_g1_ms, msm_b_g2_ms;
+    float assemble_ms;    /* scalar muls, "Finish C", normalisation */
+    float total_ms;       /* "Groth16::Prover" */
+} g16_timings;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------------------------- */
+int g16_device_count(void);
+/* Creates a context bound to CUDA device `device`.  main_stream may be NULL (library-owned stream) or a cudaStream_t the
+ * caller owns (e.g. torch's current stream): all work of later calls is ordered on it. */
+int g16_ctx_create(g16_ctx** out, int device, void* main_stream);
+void g16_ctx_destroy(g16_ctx* ctx);
+const char* g16_last_error(const g16_ctx* ctx); /* ctx may be NULL: last error of g16_ctx_create on this thread */
+const char* g16_version(void);
+
+/* Uploads the proving key.  With shard_count > 1 this context keeps only the contiguous point range
+ * [rank*N/G, (rank+1)*N/G) of each query; the single points are kept by every rank.
+ * precompute != 0 additionally stores 2^(c*j) multiples of every base so that all Pippenger windows share one bucket
+ * set (trades HBM for the per-window reduction and the Horner tail). */
+int g16_ctx_load_pk(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int shard_count, int precompute);
+/* Uploads the R1CS matrices (once; proof-independent -- SURVEY 8f-1). */
+int g16_ctx_load_r1cs(g16_ctx* ctx, const g16_r1cs_view* r1cs);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------------- */
+/* create_proof_with_reduction_and_matrices(pk, r, s, matrices, num_inputs, num_constraints, full_assignment):
+ * z = full_assignment (m Montgomery elements, z[0] = 1).  reduction selects the R1CSToQAP implementation. */
+int g16_prove(g16_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64_t s[4], int reduction, g16_proof* out);
+/* Same, witness already resident on the device (g16_upload_witness): no H2D inside. */
+int g16_upload_witness(g16_ctx* ctx, const uint64_t* z);
+int g16_prove_resident(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], int reduction, g16_proof* out);
+
+/* MSM-sharded proving: every rank calls g16_prove_shard on its context (loaded with its shard), the G partials are
+ * gathered (one small NCCL gather by the host glue) and rank 0 calls g16_prove_combine. */
+int g16_prove_shard(g16_ctx* ctx, const uint64_t* z, int reduction, g16_partial* out);
+int g16_prove_combine(g16_ctx* ctx, const g16_partial* partials, int count, const uint64_t r[4], const uint64_t s[4],
+                      g16_proof* out);
+/* Device pointer + byte size of this context's partial buffer, for a device-side NCCL gather. */
+int g16_partial_dev(g16_ctx* ctx, void** dev_ptr, size_t* bytes);
+int g16_prove_shard_dev(g16_ctx* ctx, int reduction);          /* witness resident; result left in the device partial */
+int g16_prove_combine_dev(g16_ctx* ctx, const void* dev_partials, int count, const uint64_t r[4], const uint64_t s[4],
+                          g16_proof* out);
+
+/* witness_map_from_matrices: h_out receives n Montgomery elements (n = domain size, returned in *n_out). */
+int g16_witness_map(g16_ctx* ctx, const uint64_t* z, int reduction, uint64_t* h_out, size_t h_capacity, size_t* n_out);
+int g16_domain_size(g16_ctx* ctx, size_t* n_out);
+int g16_get_timings(g16_ctx* ctx, g16_timings* out);
+
+/* ---- building blocks (parity hooks and the synthetic sweep) ------------------------------------------------------- */
+/* Sigma scalars[i] * points[i]; scalars Montgomery Fr; result affine Montgomery (+ infinity flag). */
+int g16_msm_g1(g16_ctx* ctx, const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t out[8], int* out_inf);
+int g16_msm_g2(g16_ctx* ctx, const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t out[16], int* out_inf);
+/* Resident variant: bases stay on the device in `slot` (0..7); scalars_dev is a device pointer.  window_bits = 0 picks
+ * the default; precompute as in g16_ctx_load_pk. */
+int g16_msm_set_bases(g16_ctx* ctx, int slot, int group /*1|2*/, const uint64_t* points, size_t n, int window_bits,
+                      int precompute);
+int g16_msm_set_bases_dev(g16_ctx* ctx, int slot, int group, const void* points_dev, size_t n, int window_bits,
+                          int precompute);
+int g16_msm_run_dev(g16_ctx* ctx, int slot, const void* scalars_dev, size_t n, uint64_t* out, int* out_inf);
+
+/* In-place NTT over Fr of size 2^log_n, natural order in and out (arkworks semantics): inverse includes 1/n; coset
+ * applies the shift g = Fr::GENERATOR = 5 (fft: scale then transform; ifft: transform then unscale). */
+int g16_ntt(g16_ctx* ctx, uint64_t* data, unsigned log_n, int inverse, int coset);
+int g16_ntt_dev(g16_ctx* ctx, void* data_dev, unsigned log_n, int inverse, int coset);
+
+/* Element-wise field arithmetic on n elements (Fq2: 8 x u64 per element). */
+int g16_field_op(g16_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+
+/* k_i * G for the canonical generators (generator.rs:34-35); scalars Montgomery Fr; outputs affine Montgomery. */
+int g16_fixed_base_g1(g16_ctx* ctx, const uint64_t* scalars, size_t n, uint64_t* out_points);
+int g16_fixed_base_g2(g16_ctx* ctx, const uint64_t* scalars, size_t n, uint64_t* out_points);
+int g16_fixed_base_g1_dev(g16_ctx* ctx, const void* scalars_dev, size_t n, void* out_points_dev);
+int g16_fixed_base_g2_dev(g16_ctx* ctx, const void* scalars_dev, size_t n, void* out_points_dev);
+
+/* Sparse R1CS evaluation a = A z, b = B z, c = C z over the loaded matrices (evaluate_constraint,
+ * r1cs_to_qap.rs:16-45); outputs nc Montgomery elements each (any may be NULL). */
+int g16_r1cs_eval(g16_ctx* ctx, const uint64_t* z, uint64_t* az, uint64_t* bz, uint64_t* cz);
+
+/* ---- device memory + micro-benchmarks ------------------------------------------------------------------------------ */
+int g16_dev_alloc(g16_ctx* ctx, size_t bytes, void** dev_ptr);
+int g16_dev_free(g16_ctx* ctx, void* dev_ptr);
+int g16_dev_upload(g16_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+int g16_dev_download(g16_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+int g16_sync(g16_ctx* ctx);
+/* Integer-pipe peak probes: returns achieved giga-operations per second of (0) IMAD 32-bit, (1) IMAD.WIDE.U32 chains,
+ * (2) Fr Montgomery multiplications, (3) Fq Montgomery multiplications -- the measured denominators of the integer
+ * roofline (MEASURED_PEAKS.json carries none). */
+int g16_bench_int_pipe(g16_ctx* ctx, int which, double* gops_out);
+/* Number of kernels this library has launched on this context since creation (for the bench's gpu_launches claim). */
+uint64_t g16_launch_count(const g16_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G16_B200_H */
