@@ -78,6 +78,7 @@ int g16_ctx_create(g16_ctx** out, int device, void* main_stream) {
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev_t[i]);
+    for (int i = 0; i < 10 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev_acc[i]);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_small, 4096);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_partial, sizeof(g16_partial));
     if (e != cudaSuccess) {
@@ -131,6 +132,8 @@ void g16_ctx_destroy(g16_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (int i = 0; i < 16; i++)
         if (ctx->ev_t[i]) cudaEventDestroy(ctx->ev_t[i]);
+    for (int i = 0; i < 10; i++)
+        if (ctx->ev_acc[i]) cudaEventDestroy(ctx->ev_acc[i]);
     if (ctx->own_main && ctx->main) cudaStreamDestroy(ctx->main);
     delete ctx;
 }
@@ -175,7 +178,8 @@ int g16_dev_download(g16_ctx* ctx, void* dst, const void* src, size_t bytes) {
 // ---- building blocks ----------------------------------------------------------------------------------------------------
 int g16_field_op(g16_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
     if (!ctx || !a || !out) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "field_op: null pointer") : G16_ERR_BAD_ARG;
-    bool binary = (op == G16_OP_MUL || op == G16_OP_ADD || op == G16_OP_SUB);
+    bool bcast = (op == G16_OP_MUL_BCAST || op == G16_OP_ADD_BCAST);
+    bool binary = (op == G16_OP_MUL || op == G16_OP_ADD || op == G16_OP_SUB || bcast);
     if (binary && !b) return set_err(ctx, G16_ERR_BAD_ARG, "field_op: binary op needs b");
     if (n == 0) return G16_OK;
     Guard g(ctx);
@@ -186,7 +190,7 @@ int g16_field_op(g16_ctx* ctx, int field, int op, const uint64_t* a, const uint6
     G16_CUDA(ctx, cudaMalloc(&dc, n * esz));
     int rc = G16_OK;
     cudaMemcpyAsync(da, a, n * esz, cudaMemcpyHostToDevice, ctx->main);
-    if (binary) cudaMemcpyAsync(db, b, n * esz, cudaMemcpyHostToDevice, ctx->main);
+    if (binary) cudaMemcpyAsync(db, b, (bcast ? 1 : n) * esz, cudaMemcpyHostToDevice, ctx->main);
     rc = field_op_dev(ctx, field, op, da, db, dc, n, ctx->main);
     if (rc == G16_OK) {
         cudaMemcpyAsync(out, dc, n * esz, cudaMemcpyDeviceToHost, ctx->main);
@@ -247,7 +251,7 @@ static int msm_host(g16_ctx* ctx, int group, const uint64_t* points, const uint6
     cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, ctx->main);
     MsmBases mb;
     MsmScratch sc;
-    int rc = msm_set_bases(ctx, &mb, &sc, group, dp, n, 0, false, ctx->main);
+    int rc = msm_set_bases(ctx, &mb, &sc, group, dp, n, ctx->opt_window_bits, false, ctx->main);
     if (rc == G16_OK) rc = msm_run(ctx, &mb, &sc, ds, n, ctx->main);
     if (rc == G16_OK) rc = xyzz_to_affine_host(ctx, group, sc.result, out, out_inf, ctx->main);
     cudaStreamSynchronize(ctx->main);
@@ -463,7 +467,7 @@ static int load_query(g16_ctx* ctx, int qi, int group, const uint64_t* pts, size
         if (e != cudaSuccess) rc = set_err(ctx, G16_ERR_CUDA, "pk upload: %s", cudaGetErrorString(e));
         if (rc == G16_OK && enc == G16_ENC_CANONICAL) rc = convert_mont_dev(ctx, G16_FIELD_FQ, stage, cnt * (pb / 32), true, ctx->main);
     }
-    if (rc == G16_OK) rc = msm_set_bases(ctx, &ctx->q[qi], &ctx->scratch[qi], group, stage, cnt, 0, precompute != 0, ctx->main);
+    if (rc == G16_OK) rc = msm_set_bases(ctx, &ctx->q[qi], &ctx->scratch[qi], group, stage, cnt, ctx->opt_window_bits, precompute != 0, ctx->main);
     cudaStreamSynchronize(ctx->main);
     cudaFree(stage);
     return rc;
@@ -539,13 +543,15 @@ static int prove_shard_streams(g16_ctx* ctx, int reduction) {
     // z-only MSMs on the side streams: l (aux = z[ni..]), a / b_g1 / b_g2 (assignment = z[1..])   (prover.rs:70-74,89-117)
     const int side_q[4] = {Q_L, Q_A, Q_B1, Q_B2};
     for (int k = 0; k < 4; k++) {
-        cudaStream_t st = ctx->side[k];
+        cudaStream_t st = ctx->opt_serialize ? main : ctx->side[k];
         int qi = side_q[k];
-        G16_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+        cudaEvent_t ea0 = ctx->opt_kernel_events ? ctx->ev_acc[2 * qi] : nullptr;
+        cudaEvent_t ea1 = ctx->opt_kernel_events ? ctx->ev_acc[2 * qi + 1] : nullptr;
+        if (!ctx->opt_serialize) G16_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
         const Fr* sc = ctx->d_z + (qi == Q_L ? ctx->ni : 1) + ctx->sh_lo[qi];
         size_t cnt = ctx->sh_hi[qi] - ctx->sh_lo[qi];
         G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * qi], st));
-        G16_TRY(msm_run(ctx, &ctx->q[qi], &ctx->scratch[qi], sc, cnt, st));
+        G16_TRY(msm_run(ctx, &ctx->q[qi], &ctx->scratch[qi], sc, cnt, st, ea0, ea1));
         void* dst = qi == Q_L ? (void*)&part->l : qi == Q_A ? (void*)&part->a : qi == Q_B1 ? (void*)&part->b1 : (void*)&part->b2;
         size_t bytes = qi == Q_B2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
         if (cnt && ctx->scratch[qi].result)
@@ -553,7 +559,7 @@ static int prove_shard_streams(g16_ctx* ctx, int reduction) {
         else
             G16_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, st));
         G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * qi], st));
-        G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], st));
+        if (!ctx->opt_serialize) G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], st));
     }
     // main: witness map, then the h MSM over h[lo..hi)  (prover.rs:63-66; the zip drops h[n-1], generator.rs:178)
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[0], main));
@@ -562,14 +568,16 @@ static int prove_shard_streams(g16_ctx* ctx, int reduction) {
     {
         size_t cnt = ctx->sh_hi[Q_H] - ctx->sh_lo[Q_H];
         G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * Q_H], main));
-        G16_TRY(msm_run(ctx, &ctx->q[Q_H], &ctx->scratch[Q_H], ctx->d_a + ctx->sh_lo[Q_H], cnt, main));
+        G16_TRY(msm_run(ctx, &ctx->q[Q_H], &ctx->scratch[Q_H], ctx->d_a + ctx->sh_lo[Q_H], cnt, main,
+                        ctx->opt_kernel_events ? ctx->ev_acc[0] : nullptr, ctx->opt_kernel_events ? ctx->ev_acc[1] : nullptr));
         if (cnt && ctx->scratch[Q_H].result)
             G16_CUDA(ctx, cudaMemcpyAsync(&part->h, ctx->scratch[Q_H].result, sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, main));
         else
             G16_CUDA(ctx, cudaMemsetAsync(&part->h, 0, sizeof(G1XYZZ), main));
         G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * Q_H], main));
     }
-    for (int k = 0; k < 4; k++) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[k], 0));
+    if (!ctx->opt_serialize)
+        for (int k = 0; k < 4; k++) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[k], 0));
     return G16_OK;
 }
 
@@ -589,6 +597,14 @@ static void collect_timings(g16_ctx* ctx, bool with_asm) {
     ctx->tm.msm_b_g1_ms = el(8, 9);
     ctx->tm.msm_b_g2_ms = el(10, 11);
     ctx->tm.h2d_ms = el(14, 0);
+    for (int k = 0; k < 5; k++) {
+        float ms = -1;
+        if (ctx->opt_kernel_events && cudaEventElapsedTime(&ms, ctx->ev_acc[2 * k], ctx->ev_acc[2 * k + 1]) != cudaSuccess) {
+            cudaGetLastError();
+            ms = -1;
+        }
+        ctx->tm.acc_ms[k] = ms;
+    }
     if (with_asm) {
         ctx->tm.assemble_ms = el(12, 13);
         ctx->tm.total_ms = el(14, 13);
@@ -668,6 +684,13 @@ int g16_partial_dev(g16_ctx* ctx, void** dev_ptr, size_t* bytes) {
     return G16_OK;
 }
 
+int g16_copy_partial_dev(g16_ctx* ctx, void* dst_dev) {
+    if (!ctx || !dst_dev) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_CUDA(ctx, cudaMemcpyAsync(dst_dev, ctx->d_partial, sizeof(g16_partial), cudaMemcpyDeviceToDevice, ctx->main));
+    return G16_OK;
+}
+
 int g16_prove_combine_dev(g16_ctx* ctx, const void* dev_partials, int count, const uint64_t r[4], const uint64_t s[4],
                           g16_proof* out) {
     if (!ctx || !dev_partials || !r || !s || !out || count < 1) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "prove_combine: bad argument") : G16_ERR_BAD_ARG;
@@ -687,6 +710,36 @@ int g16_prove_combine(g16_ctx* ctx, const g16_partial* partials, int count, cons
         G16_CUDA(ctx, cudaMemcpy(d, partials, sizeof(g16_partial) * (size_t)count, cudaMemcpyHostToDevice));
     }
     int rc = g16_prove_combine_dev(ctx, d, count, r, s, out);
+    cudaFree(d);
+    return rc;
+}
+
+int g16_set_option(g16_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!strcmp(key, "serialize")) ctx->opt_serialize = value;
+    else if (!strcmp(key, "kernel_events")) ctx->opt_kernel_events = value;
+    else if (!strcmp(key, "window_bits")) ctx->opt_window_bits = value;
+    else return set_err(ctx, G16_ERR_BAD_ARG, "unknown option '%s'", key);
+    return G16_OK;
+}
+
+int g16_pow_table(g16_ctx* ctx, const uint64_t base[4], const uint64_t scale[4], size_t n, uint64_t* out) {
+    if (!ctx || !base || !scale || (n && !out)) return G16_ERR_BAD_ARG;
+    if (n == 0) return G16_OK;
+    if (n >= ((size_t)1 << 32)) return set_err(ctx, G16_ERR_BAD_ARG, "pow_table: n too large");
+    Guard g(ctx);
+    Fr b, s;
+    memcpy(&b, base, 32);
+    memcpy(&s, scale, 32);
+    Fr* d;
+    G16_CUDA(ctx, cudaMalloc((void**)&d, n * 32));
+    int rc = pow_table_dev(ctx, d, n, b, s, ctx->main);
+    if (rc == G16_OK) {
+        cudaMemcpyAsync(out, d, n * 32, cudaMemcpyDeviceToHost, ctx->main);
+        cudaError_t e = cudaStreamSynchronize(ctx->main);
+        if (e != cudaSuccess) rc = set_err(ctx, G16_ERR_CUDA, "pow_table: %s", cudaGetErrorString(e));
+    }
     cudaFree(d);
     return rc;
 }

@@ -17,6 +17,8 @@ __global__ void k_field_op(int op, const F* __restrict__ a, const F* __restrict_
             case G16_OP_NEG: r = x.neg(); break;
             case G16_OP_INV: r = x.inverse(); break;
             case G16_OP_SQR: r = x.sqr(); break;
+            case G16_OP_MUL_BCAST: r = x * b[0]; break;
+            case G16_OP_ADD_BCAST: r = x + b[0]; break;
             default: r = x; break;
         }
         out[i] = r;

@@ -110,6 +110,8 @@ struct g16_ctx {
     void* d_partial = nullptr;  // g16_partial on the device
     void* d_small = nullptr;    // small device scratch for assembly
     g16_timings tm = {};
+    int opt_serialize = 0, opt_kernel_events = 0, opt_window_bits = 0;
+    cudaEvent_t ev_acc[10] = {};
 
     // generic MSM slots
     g16::MsmBases slot[g16::kMsmSlots];
@@ -164,6 +166,7 @@ int ntt_dif(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* p
 int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* post, const Fr* post_scalar,
             cudaStream_t st);
 int bitrev_permute(g16_ctx* ctx, Fr* data, unsigned log_n, cudaStream_t st);
+int pow_table_dev(g16_ctx* ctx, Fr* out, size_t n, Fr base, Fr scale, cudaStream_t st);
 int ntt_api(g16_ctx* ctx, Fr* data_dev, unsigned log_n, int inverse, int coset, cudaStream_t st);
 
 // witness.cu ------------------------------------------------------------------------------------------------------------
@@ -176,7 +179,8 @@ int msm_set_bases(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, int group, const v
                   bool precomp, cudaStream_t st);
 void msm_free(MsmBases* mb, MsmScratch* sc);
 // runs Pippenger over the first n bases with device scalars (Montgomery Fr); leaves the XYZZ result in sc->result
-int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st);
+int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st,
+            cudaEvent_t ev_acc0 = nullptr, cudaEvent_t ev_acc1 = nullptr);
 int fixed_base_dev(g16_ctx* ctx, int group, const Fr* scalars_dev, size_t n, void* out_pts_dev, cudaStream_t st);
 
 // assemble.cu -----------------------------------------------------------------------------------------------------------

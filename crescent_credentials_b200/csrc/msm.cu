@@ -628,7 +628,8 @@ int msm_set_bases(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, int group, const v
 }
 
 template <class F>
-static int msm_run_t(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars, size_t n, cudaStream_t st) {
+static int msm_run_t(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars, size_t n, cudaStream_t st, cudaEvent_t ev0,
+                     cudaEvent_t ev1) {
     XYZZ<F>* result = (XYZZ<F>*)sc->result;
     if (n > mb->n) return set_err(ctx, G16_ERR_BAD_ARG, "msm: %zu scalars for %zu bases", n, mb->n);
     if (n == 0 || mb->n == 0) {
@@ -678,8 +679,10 @@ static int msm_run_t(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scala
     {
         size_t want = (tcap + 127) / 128;
         unsigned grid = (unsigned)(want < (size_t)kNumSMs * 8 ? want : (size_t)kNumSMs * 8);
+        if (ev0) G16_CUDA(ctx, cudaEventRecord(ev0, st));
         G16_LAUNCH(ctx, k_accumulate<F>, grid, 128, 0, st, (const Affine<F>*)mb->pts, vals, tkeys, tvals, t_start, t_len,
                    (XYZZ<F>*)sc->partial, tcap);
+        if (ev1) G16_CUDA(ctx, cudaEventRecord(ev1, st));
     }
     // 6. combine task partials per bucket
     {
@@ -706,9 +709,10 @@ static int msm_run_t(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scala
     return G16_OK;
 }
 
-int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st) {
-    if (mb->group == 1) return msm_run_t<Fq>(ctx, mb, sc, scalars_dev, n, st);
-    if (mb->group == 2) return msm_run_t<Fq2>(ctx, mb, sc, scalars_dev, n, st);
+int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st, cudaEvent_t ev0,
+            cudaEvent_t ev1) {
+    if (mb->group == 1) return msm_run_t<Fq>(ctx, mb, sc, scalars_dev, n, st, ev0, ev1);
+    if (mb->group == 2) return msm_run_t<Fq2>(ctx, mb, sc, scalars_dev, n, st, ev0, ev1);
     return set_err(ctx, G16_ERR_BAD_ARG, "msm: bases not set");
 }
 

@@ -65,8 +65,14 @@ __global__ void k_pow_table(Fr* __restrict__ out, size_t n, PowLadder lad, Fr sc
     }
 }
 
+int pow_table_dev(g16_ctx* ctx, Fr* out, size_t n, Fr base, Fr scale, cudaStream_t st);
 static int make_pow_table(g16_ctx* ctx, Fr** out, size_t n, Fr base, Fr scale, cudaStream_t st) {
     G16_TRY(dev_alloc(ctx, out, n));
+    return pow_table_dev(ctx, *out, n, base, scale, st);
+}
+int pow_table_dev(g16_ctx* ctx, Fr* dst, size_t n, Fr base, Fr scale, cudaStream_t st) {
+    Fr** out = &dst;
+    if (n == 0) return G16_OK;
     PowLadder lad;
     Fr b = base;
     for (int k = 0; k < 32; k++) {

@@ -16,7 +16,7 @@ ERR_DEGREE_TOO_LARGE, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_VANISHI
 REDUCTION_LIBSNARK, REDUCTION_CIRCOM = 0, 1
 ENC_MONTGOMERY, ENC_CANONICAL = 0, 1
 FIELD_FR, FIELD_FQ, FIELD_FQ2 = 0, 1, 2
-OP_MUL, OP_ADD, OP_SUB, OP_NEG, OP_INV, OP_TO_MONT, OP_FROM_MONT, OP_SQR = range(8)
+OP_MUL, OP_ADD, OP_SUB, OP_NEG, OP_INV, OP_TO_MONT, OP_FROM_MONT, OP_SQR, OP_MUL_BCAST, OP_ADD_BCAST = range(10)
 PARTIAL_U64 = 4 * 16 + 32
 
 # every symbol include/g16_b200.h declares (tests check the library exports all of them)
@@ -27,7 +27,8 @@ EXPORTS = [
     "g16_domain_size", "g16_get_timings", "g16_msm_g1", "g16_msm_g2", "g16_msm_set_bases", "g16_msm_set_bases_dev",
     "g16_msm_run_dev", "g16_ntt", "g16_ntt_dev", "g16_field_op", "g16_fixed_base_g1", "g16_fixed_base_g2",
     "g16_fixed_base_g1_dev", "g16_fixed_base_g2_dev", "g16_r1cs_eval", "g16_dev_alloc", "g16_dev_free",
-    "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count",
+    "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count", "g16_set_option",
+    "g16_pow_table", "g16_copy_partial_dev",
 ]
 
 _u64p = C.POINTER(C.c_uint64)
@@ -64,10 +65,13 @@ class Partial(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "witness_map_ms", "msm_h_ms", "msm_l_ms", "msm_a_ms",
-                                         "msm_b_g1_ms", "msm_b_g2_ms", "assemble_ms", "total_ms")]
+                                         "msm_b_g1_ms", "msm_b_g2_ms", "assemble_ms", "total_ms")] + [
+        ("acc_ms", C.c_float * 5), ("_reserved", C.c_float * 3)]
 
     def as_dict(self):
-        return {n: float(getattr(self, n)) for n, _ in self._fields_}
+        d = {n: float(getattr(self, n)) for n, _ in self._fields_[:9]}
+        d["acc_ms"] = dict(zip(("h", "l", "a", "b_g1", "b_g2"), (float(x) for x in self.acc_ms)))
+        return d
 
 
 class G16Error(RuntimeError):
@@ -109,6 +113,7 @@ def load_library() -> C.CDLL:
     lib.g16_prove_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
     lib.g16_partial_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.g16_prove_shard_dev.argtypes = [C.c_void_p, C.c_int]
+    lib.g16_copy_partial_dev.argtypes = [C.c_void_p, C.c_void_p]
     lib.g16_prove_combine_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
     lib.g16_witness_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.g16_domain_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
@@ -130,6 +135,8 @@ def load_library() -> C.CDLL:
     lib.g16_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.g16_sync.argtypes = [C.c_void_p]
     lib.g16_bench_int_pipe.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    lib.g16_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    lib.g16_pow_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     _lib = lib
     return lib
 
@@ -154,7 +161,7 @@ class Context:
         if rc != G16_OK:
             raise G16Error(rc, self.lib.g16_last_error(None).decode())
         self.h = h
-        self._keep = []
+        self.device = device
 
     def close(self):
         if getattr(self, "h", None):
@@ -211,6 +218,16 @@ class Context:
         out = np.zeros((scalars.shape[0], pw), dtype=np.uint64)
         fn = self.lib.g16_fixed_base_g1 if group == 1 else self.lib.g16_fixed_base_g2
         self.check(fn(self.h, _ptr(scalars), scalars.shape[0], _ptr(out)))
+        return out
+
+    def set_option(self, key: str, value: int):
+        self.check(self.lib.g16_set_option(self.h, key.encode(), int(value)))
+
+    def pow_table(self, base: np.ndarray, scale: np.ndarray, n: int) -> np.ndarray:
+        base = np.ascontiguousarray(base, dtype=np.uint64)
+        scale = np.ascontiguousarray(scale, dtype=np.uint64)
+        out = np.empty((n, 4), dtype=np.uint64)
+        self.check(self.lib.g16_pow_table(self.h, _ptr(base), _ptr(scale), n, _ptr(out)))
         return out
 
     def bench_int_pipe(self, which: int) -> float:
@@ -324,6 +341,9 @@ class Context:
 
     def prove_shard_dev(self, reduction=REDUCTION_LIBSNARK):
         self.check(self.lib.g16_prove_shard_dev(self.h, reduction))
+
+    def copy_partial_dev(self, dst_dev: int):
+        self.check(self.lib.g16_copy_partial_dev(self.h, C.c_void_p(dst_dev)))
 
     def partial_dev(self):
         p = C.c_void_p()

@@ -60,6 +60,8 @@ extern "C" {
 #define G16_OP_TO_MONT 5
 #define G16_OP_FROM_MONT 6
 #define G16_OP_SQR 7
+#define G16_OP_MUL_BCAST 8 /* out[i] = a[i] * b[0] */
+#define G16_OP_ADD_BCAST 9 /* out[i] = a[i] + b[0] */
 
 typedef struct g16_ctx g16_ctx;
 
@@ -112,6 +114,9 @@ typedef struct g16_timings {
     float msm_h_ms, msm_l_ms, msm_a_ms, msm_b_g1_ms, msm_b_g2_ms;
     float assemble_ms;    /* scalar muls, "Finish C", normalisation */
     float total_ms;       /* "Groth16::Prover" */
+    /* with option "kernel_events": duration of the bucket-accumulation kernel of each MSM (h, l, a, b_g1, b_g2) */
+    float acc_ms[5];
+    float _reserved[3];
 } g16_timings;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------------- */
@@ -147,6 +152,7 @@ int g16_prove_combine(g16_ctx* ctx, const g16_partial* partials, int count, cons
 /* Device pointer + byte size of this context's partial buffer, for a device-side NCCL gather. */
 int g16_partial_dev(g16_ctx* ctx, void** dev_ptr, size_t* bytes);
 int g16_prove_shard_dev(g16_ctx* ctx, int reduction);          /* witness resident; result left in the device partial */
+int g16_copy_partial_dev(g16_ctx* ctx, void* dst_dev);         /* stream-ordered D2D copy of the partial (e.g. into an NCCL buffer) */
 int g16_prove_combine_dev(g16_ctx* ctx, const void* dev_partials, int count, const uint64_t r[4], const uint64_t s[4],
                           g16_proof* out);
 
@@ -154,6 +160,10 @@ int g16_prove_combine_dev(g16_ctx* ctx, const void* dev_partials, int count, con
 int g16_witness_map(g16_ctx* ctx, const uint64_t* z, int reduction, uint64_t* h_out, size_t h_capacity, size_t* n_out);
 int g16_domain_size(g16_ctx* ctx, size_t* n_out);
 int g16_get_timings(g16_ctx* ctx, g16_timings* out);
+/* Options: "serialize" = 1 runs every stage on the main stream (no overlap; for per-kernel timing),
+ * "kernel_events" = 1 brackets the bucket-accumulation kernels with CUDA events (fills g16_timings.acc_ms),
+ * "window_bits" = c forces the Pippenger window of bases loaded afterwards (0 = automatic). */
+int g16_set_option(g16_ctx* ctx, const char* key, int value);
 
 /* ---- building blocks (parity hooks and the synthetic sweep) ------------------------------------------------------- */
 /* Sigma scalars[i] * points[i]; scalars Montgomery Fr; result affine Montgomery (+ infinity flag). */
@@ -180,6 +190,9 @@ int g16_fixed_base_g1(g16_ctx* ctx, const uint64_t* scalars, size_t n, uint64_t*
 int g16_fixed_base_g2(g16_ctx* ctx, const uint64_t* scalars, size_t n, uint64_t* out_points);
 int g16_fixed_base_g1_dev(g16_ctx* ctx, const void* scalars_dev, size_t n, void* out_points_dev);
 int g16_fixed_base_g2_dev(g16_ctx* ctx, const void* scalars_dev, size_t n, void* out_points_dev);
+
+/* out[i] = scale * base^i, i < n (Montgomery Fr) -- powers of tau for the key generator (r1cs_to_qap.rs:215-225). */
+int g16_pow_table(g16_ctx* ctx, const uint64_t base[4], const uint64_t scale[4], size_t n, uint64_t* out);
 
 /* Sparse R1CS evaluation a = A z, b = B z, c = C z over the loaded matrices (evaluate_constraint,
  * r1cs_to_qap.rs:16-45); outputs nc Montgomery elements each (any may be NULL). */
