@@ -213,3 +213,31 @@ def test_errors_are_loud(gpu_ctx):
 def test_int_pipe_probe(gpu_ctx):
     for which in range(4):
         assert gpu_ctx.bench_int_pipe(which) > 1.0
+
+
+@pytest.mark.parametrize("name", ["rand100", "rand300", "dummy924_nozk"])
+def test_golden_prove_precomputed_windows(name):
+    """Same golden proofs with the 2^(c*w) base tables (single bucket set, no Horner tail)."""
+    meta, r1cs_bytes, pk_bytes = load_golden(name)
+    mats = load_matrices(r1cs_bytes)
+    pk = g.ProvingKey.deserialize_uncompressed_unchecked(pk_bytes)
+    prover = g.Groth16(0, precompute=True)
+    try:
+        z = [int(v, 16) for v in meta["z"]]
+        proof = prover.create_proof_with_reduction_and_matrices(pk, int(meta["r"], 16), int(meta["s"], 16), mats,
+                                                                mats.num_instance_variables, mats.num_constraints, z)
+        assert proof.serialize_uncompressed().hex() == meta["proof_uncompressed"]
+    finally:
+        prover.close()
+
+
+@pytest.mark.parametrize("c", [4, 7, 13, 18])
+def test_msm_window_sizes(gpu_ctx, c):
+    n = 200
+    pts, sc = _points(o.G1, n, 41), _scalars(n, 42)
+    gpu_ctx.set_option("window_bits", c)
+    try:
+        out, inf = gpu_ctx.msm(1, g.g1_points_to_mont(pts), g.fr_to_mont(sc))
+    finally:
+        gpu_ctx.set_option("window_bits", 0)
+    assert g.g1_from_mont(out, inf) == o.G1.to_affine(o.G1.msm(pts, sc))

@@ -1,0 +1,129 @@
+"""CPU tests of host-side logic: R1CS -> CSR flattening, proving-key (de)serialisation, synthetic generator determinism,
+MSM shard partitioning, and the 2-rank (gloo) gather used by the sharded prover."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import coracle as c
+import pyref as o
+from conftest import load_golden
+from crescent_credentials_b200 import ffi, generator, synth
+from crescent_credentials_b200 import groth16 as g
+from crescent_credentials_b200.r1cs import load_matrices
+from crescent_credentials_b200.sharded import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_csr_flattening_sums_duplicates_and_drops_zeros():
+    cons = [([(1, 5), (1, 7), (2, 3)], [(0, 1)], [(3, o.R_MOD - 4), (3, 4)]),   # dup wire 1 -> 12; wire 3 cancels to 0
+            ([], [(2, 2)], [])]
+    data = o.write_r1cs(4, 1, 0, 2, cons)
+    m = load_matrices(data)
+    assert m.num_instance_variables == 2 and m.num_witness_variables == 2 and m.num_constraints == 2
+    assert list(m.row_ptr[0]) == [0, 2, 2] and list(m.col[0]) == [1, 2]
+    assert g.limbs_to_ints(m.val[0]) == [12, 3]
+    assert list(m.row_ptr[2]) == [0, 0, 0]
+    om = o.r1cs_to_matrices(o.read_r1cs(data))
+    assert om.a == [[(12, 1), (3, 2)], []] and om.c == [[], []]
+
+
+def test_pk_deserialisation_round_trip():
+    meta, _, pk_bytes = load_golden("rand100")
+    pk = g.ProvingKey.deserialize_uncompressed_unchecked(pk_bytes)
+    assert pk.encoding == ffi.ENC_CANONICAL
+    n = meta["domain_size"]
+    assert pk.arrays["h_query"].shape == (n - 1, 8)           # h_query has n-1 points (generator.rs:174-179)
+    assert pk.arrays["a_query"].shape[0] == meta["num_instance"] + meta["num_witness"]
+    assert pk.arrays["l_query"].shape[0] == meta["num_witness"]
+    # canonical coordinates lie on the curve; infinities are zeros
+    for row in pk.arrays["b_g1_query"]:
+        x, y = g.limbs_to_ints(row.reshape(2, 4))
+        assert (x, y) == (0, 0) or o.G1.is_on_curve((x, y))
+    with pytest.raises(ValueError):
+        g.ProvingKey.deserialize_uncompressed_unchecked(pk_bytes + b"\0")
+
+
+def test_synthetic_streams_are_deterministic_and_match_scalar_splitmix():
+    a = synth.stream(0xC0FFEE, 0x10, 1000)
+    assert np.array_equal(a, synth.stream(0xC0FFEE, 0x10, 1000))
+    base = (0xC0FFEE ^ (0x10 << 40)) & 0xFFFFFFFFFFFFFFFF
+    assert int(a[17]) == o.splitmix64(17 ^ base)
+    z = synth.witness_canonical(1, 5000, "circom")
+    ints = g.limbs_to_ints(z)
+    assert ints[0] == 1 and all(v < o.R_MOD for v in ints)
+    frac_bits = sum(v in (0, 1) for v in ints) / len(ints)
+    assert 0.8 < frac_bits < 0.9
+    rp, col, val = synth._matrix(3, 0x10, 2000, 1900, 4.7, 1, 0)
+    assert rp[-1] == len(col) == len(val) and col.max() < 1900
+    assert 3.5 < float(rp[-1]) / 2000 < 6.0
+    assert all(v < o.R_MOD for v in g.limbs_to_ints(val[:500]))
+
+
+def test_transpose_csr():
+    rp = np.array([0, 2, 3, 3], dtype=np.uint64)
+    col = np.array([2, 0, 2], dtype=np.uint32)
+    val = np.arange(12, dtype=np.uint64).reshape(3, 4)
+    tp, tc, tv = generator.transpose_csr(3, 4, rp, col, val)
+    assert list(tp) == [0, 1, 1, 3, 3] and list(tc) == [0, 0, 1]
+    assert np.array_equal(tv, val[[1, 0, 2]])
+
+
+def test_shard_ranges_partition_every_query():
+    for total in (0, 1, 7, 1_449_999, 2_097_151):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from crescent_credentials_b200.sharded import gather_partials
+    # each rank contributes a recognisable 96-word partial; rank 0 must see them in rank order
+    mine = torch.full((ffi.PARTIAL_U64,), rank + 1, dtype=torch.int64)
+    allp = gather_partials(mine, world)
+    if rank == 0:
+        q.put([int(allp[r, 0]) for r in range(world)] + [tuple(allp.shape)])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather_of_partials():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got == [1, 2, (2, ffi.PARTIAL_U64)]
+
+
+def test_sharded_msm_partials_add_up_on_cpu():
+    """The sharding identity the multi-GPU path relies on: MSM over [0,N) == sum of MSMs over the rank ranges
+    (checked with the CPU oracle; the GPU version of this test is in test_gpu_sharded.py)."""
+    ks = [o.stream_fr(0x51, i) for i in range(97)]
+    pts = c.fixed_base(1, g.fr_to_mont(ks))
+    sc_int = [o.stream_fr(0x52, i) for i in range(97)]
+    sc = g.fr_to_mont(sc_int)
+    full = g.g1_from_mont(c.msm(1, pts, sc))
+    acc = None
+    for r in range(4):
+        lo, hi = shard_range(97, r, 4)
+        acc = o.G1.add(acc, g.g1_from_mont(c.msm(1, pts[lo:hi], sc[lo:hi])))
+    assert acc == full

@@ -1,0 +1,219 @@
+"""CPU tests: pin the oracles to every byte-level golden the reference tree holds for this path, to each other, and to
+the committed fixtures.  (The reference holds no golden proof / H vector / MSM output -- SURVEY 8c.)"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import coracle as c
+import pyref as o
+from conftest import GOLDEN, GOLDEN_NAMES, load_golden
+from crescent_credentials_b200 import groth16 as g
+from crescent_credentials_b200.r1cs import R1CSFile, load_matrices
+
+# forks/circom-compat/src/zkey.rs:397-402  (snarkjs curve.G1.F.one, Montgomery LE)
+FQ_ONE_BUF = bytes([157, 13, 143, 197, 141, 67, 93, 211, 61, 11, 199, 245, 40, 235, 120, 10, 44, 70, 121, 120, 111, 163, 110,
+                    102, 47, 223, 7, 154, 193, 119, 10, 14])
+# zkey.rs:408-415 (G1 generator, Montgomery LE x||y)
+G1_BUF = bytes([157, 13, 143, 197, 141, 67, 93, 211, 61, 11, 199, 245, 40, 235, 120, 10, 44, 70, 121, 120, 111, 163, 110, 102,
+                47, 223, 7, 154, 193, 119, 10, 14, 58, 27, 30, 139, 27, 135, 186, 166, 123, 22, 142, 235, 81, 214, 241, 20, 88,
+                140, 242, 240, 222, 70, 221, 204, 94, 190, 15, 52, 131, 239, 20, 28])
+# zkey.rs:421-431 (G2 generator, Montgomery LE x.c0||x.c1||y.c0||y.c1)
+G2_BUF = bytes([38, 32, 188, 2, 209, 181, 131, 142, 114, 1, 123, 73, 53, 25, 235, 220, 223, 26, 129, 151, 71, 38, 184, 251, 59,
+                80, 150, 175, 65, 56, 87, 25, 64, 97, 76, 168, 125, 115, 180, 175, 196, 216, 2, 88, 90, 221, 67, 96, 134, 47,
+                160, 82, 252, 80, 233, 9, 107, 123, 234, 58, 131, 240, 254, 20, 246, 233, 107, 136, 157, 250, 157, 97, 120, 155,
+                158, 245, 151, 210, 127, 254, 254, 125, 27, 35, 98, 26, 158, 255, 6, 66, 158, 174, 235, 126, 253, 40, 238, 86,
+                24, 199, 86, 91, 9, 100, 187, 60, 125, 50, 34, 249, 87, 220, 118, 16, 53, 51, 190, 53, 249, 85, 130, 100, 253,
+                147, 230, 160, 164, 13])
+# forks/circom-compat/src/circom/r1cs_reader.rs:266-318 (the reader's worked example)
+R1CS_SAMPLE_HEX = """
+72316373 01000000 03000000 01000000 40000000 00000000 20000000
+010000f0 93f5e143 9170b979 48e83328 5d588181 b64550b8 29a031e1 724e6430
+07000000 01000000 02000000 03000000 e8030000 00000000 03000000
+02000000 88020000 00000000
+02000000
+05000000 03000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+06000000 08000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+03000000
+00000000 02000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+02000000 14000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+03000000 0C000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+02000000
+00000000 05000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+02000000 07000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+03000000
+01000000 04000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+04000000 08000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+05000000 03000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+02000000
+03000000 2C000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+06000000 06000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+00000000
+01000000
+06000000 04000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+03000000
+00000000 06000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+02000000 0B000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+03000000 05000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+01000000
+06000000 58020000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+03000000 38000000 00000000
+00000000 00000000 03000000 00000000 0a000000 00000000 0b000000 00000000 0c000000 00000000 0f000000 00000000
+44010000 00000000
+"""
+
+
+def test_reference_byte_goldens_montgomery_encodings():
+    assert o.mont_le_bytes(1, o.Q_MOD) == FQ_ONE_BUF
+    assert o.mont_le_bytes(o.G1_GEN[0], o.Q_MOD) + o.mont_le_bytes(o.G1_GEN[1], o.Q_MOD) == G1_BUF
+    (x0, x1), (y0, y1) = o.G2_GEN
+    assert b"".join(o.mont_le_bytes(v, o.Q_MOD) for v in (x0, x1, y0, y1)) == G2_BUF
+    # the host-side marshalling of the product uses the same encoding
+    assert g.g1_points_to_mont([o.G1_GEN]).tobytes() == G1_BUF
+    assert g.g2_points_to_mont([o.G2_GEN]).tobytes() == G2_BUF
+    # and the C++ oracle agrees (to_mont of the canonical coordinates)
+    canon = g.ints_to_limbs([o.G1_GEN[0], o.G1_GEN[1], x0, x1, y0, y1])
+    assert c.field_op(1, 5, canon).tobytes() == G1_BUF + G2_BUF
+    assert o.G1.is_on_curve(o.G1_GEN) and o.G2.is_on_curve(o.G2_GEN)
+    assert o.G1.mul(o.G1_GEN, o.R_MOD - 1) == o.G1.neg(o.G1_GEN)   # group order is r
+    assert o.G2.mul(o.G2_GEN, o.R_MOD - 1) == o.G2.neg(o.G2_GEN)
+
+
+@pytest.mark.parametrize("reader", ["oracle", "product"])
+def test_reference_r1cs_sample(reader):
+    data = bytes.fromhex("".join(R1CS_SAMPLE_HEX.split()))
+    if reader == "oracle":
+        r = o.read_r1cs(data)
+        hdr = (r["version"], r["field_size"], r["n_wires"], r["n_pub_out"], r["n_pub_in"], r["n_prv_in"], r["n_labels"],
+               r["n_constraints"])
+        cons, wmap, prime = r["constraints"], r["wire_mapping"], r["prime"]
+    else:
+        f = R1CSFile(data)
+        hdr = (f.version, f.field_size, f.n_wires, f.n_pub_out, f.n_pub_in, f.n_prv_in, f.n_labels, f.n_constraints)
+        cons, wmap, prime = list(f.constraints()), list(f.wire_mapping), f.prime_size
+    # the assertions of r1cs_reader.rs:320-344
+    assert hdr == (1, 32, 7, 1, 2, 3, 0x03E8, 3)
+    assert prime == bytes.fromhex("010000f093f5e1439170b97948e833285d588181b64550b829a031e1724e6430")
+    assert len(cons) == 3 and len(cons[0][0]) == 2
+    assert cons[0][0][0] == (5, 3)
+    assert cons[2][1][0] == (0, 6)
+    assert len(cons[1][2]) == 0
+    assert len(wmap) == 7 and wmap[1] == 3
+
+
+def test_r1cs_reader_error_conventions():
+    data = bytearray(bytes.fromhex("".join(R1CS_SAMPLE_HEX.split())))
+    for mutate, msg in ((lambda d: d.__setitem__(0, 0x00), "Invalid magic number"),
+                        (lambda d: d.__setitem__(4, 0x02), "Unsupported version"),
+                        (lambda d: d.__setitem__(28, 0x02), "only supports bn256")):
+        d = bytearray(data)
+        mutate(d)
+        with pytest.raises(ValueError, match=msg):
+            R1CSFile(bytes(d))
+        with pytest.raises(ValueError, match=msg):
+            o.read_r1cs(bytes(d))
+
+
+def test_constants_rederived():
+    """SURVEY appendix constants, re-derived; these are also hard-coded in csrc/fp.cuh and oracle/g16_oracle.cpp."""
+    for p, inv32, inv64 in ((o.R_MOD, 0xEFFFFFFF, 0xC2E1F593EFFFFFFF), (o.Q_MOD, 0xE4866389, 0x87D20782E4866389)):
+        assert (-pow(p, -1, 1 << 32)) % (1 << 32) == inv32
+        assert (-pow(p, -1, 1 << 64)) % (1 << 64) == inv64
+    assert (1 << 256) % o.R_MOD == 0x0E0A77C19A07DF2F666EA36F7879462E36FC76959F60CD29AC96341C4FFFFFFB
+    assert (1 << 256) % o.Q_MOD == 0x0E0A77C19A07DF2F666EA36F7879462C0A78EB28F5C70B3DD35D438DC58F0D9D
+    assert o.FR_ROOT_2_28 == 0x2A3C09F0A58A7E8500E0A7EB8EF62ABC402D111E41112ED49BD61B6E725B19F0
+    assert pow(o.FR_ROOT_2_28, 1 << 28, o.R_MOD) == 1 and pow(o.FR_ROOT_2_28, 1 << 27, o.R_MOD) != 1
+    assert (o.R_MOD - 1) % (1 << 28) == 0 and ((o.R_MOD - 1) >> 28) % 2 == 1   # two-adicity 28
+    src = open(os.path.join(os.path.dirname(GOLDEN), "..", "crescent_credentials_b200", "csrc", "fp.cuh")).read()
+    for v in ((1 << 256) % o.R_MOD, (1 << 512) % o.R_MOD, (1 << 256) % o.Q_MOD, (1 << 512) % o.Q_MOD, o.R_MOD, o.Q_MOD):
+        for k in range(8):
+            assert "0x%08xu" % ((v >> (32 * k)) & 0xFFFFFFFF) in src
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_fixtures_cpp_oracle_reproduces_python_oracle(name):
+    """Two independent CPU implementations (big-int Python, 4x64-limb C++) agree on H and on the proof bytes of every
+    committed fixture; the fixture's proof satisfies the Groth16 equation in the exponent."""
+    meta, r1cs_bytes, pk_bytes = load_golden(name)
+    mats = load_matrices(r1cs_bytes)
+    wires = mats.num_instance_variables + mats.num_witness_variables
+    val_m = [c.field_op(0, 5, v) if len(v) else v for v in mats.val]
+    r1 = c.r1cs_struct(mats.num_constraints, mats.num_instance_variables, wires, mats.row_ptr, mats.col, val_m)
+    pk = g.ProvingKey.deserialize_uncompressed_unchecked(pk_bytes)
+    arr = {k: c.field_op(1, 5, v.reshape(-1, 4)).reshape(v.shape) for k, v in pk.arrays.items()}
+    z_int = [int(v, 16) for v in meta["z"]]
+    red = 1 if meta["reduction"] == "circom" else 0
+    proof, h, _ = c.prove(c.pk_struct(arr), r1, g.fr_to_mont(z_int), g.fr_to_mont([int(meta["r"], 16)])[0],
+                          g.fr_to_mont([int(meta["s"], 16)])[0], red, want_h=True)
+    assert g.fr_from_mont(h) == [int(v, 16) for v in meta["h"]]
+    P = g.Proof(g.g1_from_mont(proof[0]), g.g2_from_mont(proof[1]), g.g1_from_mont(proof[2]))
+    assert P.serialize_uncompressed().hex() == meta["proof_uncompressed"]
+    assert P.serialize_compressed().hex() == meta["proof_compressed"]
+    assert len(P.serialize_compressed()) == 128 and len(P.serialize_uncompressed()) == 256
+    A, B, C = (int(v, 16) for v in meta["proof_dlog"])
+    assert P.a == o.G1.mul(o.G1_GEN, A) and P.c == o.G1.mul(o.G1_GEN, C)
+
+
+def test_fixture_regeneration_is_deterministic():
+    """The committed 'silly' fixture is exactly what tests/golden/make_golden.py produces today."""
+    meta, _, pk_bytes = load_golden("silly")
+    td = o.Trapdoor(**{k: int(v, 16) for k, v in meta["trapdoor"].items()})
+    m, z = o.my_silly_circuit(o.stream_fr(7, 1), o.stream_fr(7, 2))
+    pk, qap = o.generate_parameters(m, td)
+    assert o.ser_pk(pk, False) == pk_bytes
+    proof, h, _ = o.create_proof_with_reduction_and_matrices(pk, int(meta["r"], 16), int(meta["s"], 16), m, 2, 6, z)
+    assert o.ser_proof(proof, False).hex() == meta["proof_uncompressed"]
+    assert [hex(v) for v in h] == meta["h"]
+
+
+def test_ntt_oracles_agree_and_invert():
+    for lg in (0, 1, 4, 9):
+        n = 1 << lg
+        vals = [o.stream_fr(0x99, i) for i in range(n)]
+        d = o.Domain(n)
+        x = g.fr_to_mont(vals)
+        assert g.fr_from_mont(c.ntt(x)) == d.fft(vals)
+        assert g.fr_from_mont(c.ntt(x, inverse=True, coset=True)) == d.coset_ifft(vals)
+        assert d.ifft(d.fft(vals)) == vals and d.coset_ifft(d.coset_fft(vals)) == vals
+    # evaluation semantics: fft(coeffs)[i] == poly(omega^i)
+    d = o.Domain(8)
+    coeffs = [3, 1, 4, 1, 5, 9, 2, 6]
+    ev = d.fft(coeffs)
+    for i in range(8):
+        w = d.element(i)
+        assert ev[i] == sum(cf * pow(w, k, o.R_MOD) for k, cf in enumerate(coeffs)) % o.R_MOD
+
+
+def test_msm_oracles_agree_including_edge_cases():
+    rnd = random.Random(3)
+    ks = [rnd.randrange(o.R_MOD) for _ in range(64)]
+    pts = c.fixed_base(1, g.fr_to_mont(ks))
+    pts[5] = 0   # infinity
+    sc_int = [0, 1, o.R_MOD - 1, 2] + [rnd.randrange(o.R_MOD) for _ in range(60)]
+    sc = g.fr_to_mont(sc_int)
+    want = o.G1.to_affine(o.G1.msm([g.g1_from_mont(p) for p in pts], sc_int))
+    assert g.g1_from_mont(c.msm(1, pts, sc)) == want
+    assert g.g1_from_mont(c.msm(1, pts, sc, naive=True)) == want
+    assert g.g1_from_mont(c.msm(1, pts[:0], sc[:0])) is None
+
+
+def test_domain_too_large_is_rejected():
+    with pytest.raises(ValueError):
+        o.Domain((1 << 28) + 1)
+
+
+def test_witness_map_quotient_identity():
+    """h really is the quotient: (A*B - C)(x) == h(x) * Z(x) at a random point."""
+    m, z = o.random_satisfiable_r1cs(5, 40, 3, 30)
+    h = o.witness_map_libsnark(m, 3, 40, z)
+    dom = o.Domain(43)
+    assert h[dom.n - 1] == 0
+    x = o.stream_fr(1, 1)
+    lag = dom.lagrange_at(x)
+    ev = lambda rows, extra: (sum(lag[i] * o.evaluate_constraint(rows[i], z) for i in range(40)) + extra) % o.R_MOD
+    a_x = ev(m.a, sum(lag[40 + i] * z[i] for i in range(3)))
+    b_x, c_x = ev(m.b, 0), ev(m.c, 0)
+    h_x = sum(cf * pow(x, k, o.R_MOD) for k, cf in enumerate(h)) % o.R_MOD
+    assert (a_x * b_x - c_x) % o.R_MOD == h_x * dom.vanishing(x) % o.R_MOD

@@ -1,0 +1,43 @@
+"""Profiling driver: builds the workload, warms up, then brackets ONE prove with cudaProfilerStart/Stop so that
+`ncu --profile-from-start off` sees exactly the kernels of a proof.  Also prints serialized stage timings."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from bench import build_problem  # noqa: E402
+from crescent_credentials_b200 import ffi  # noqa: E402
+from crescent_credentials_b200 import groth16 as g  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="S-rs256")
+ap.add_argument("--witness", default="uniform")
+ap.add_argument("--precompute", type=int, default=0)
+ap.add_argument("--window-bits", type=int, default=0)
+ap.add_argument("--serialize", type=int, default=1)
+ap.add_argument("--reps", type=int, default=3)
+args = ap.parse_args()
+ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream)
+if args.window_bits:
+    ctx.set_option("window_bits", args.window_bits)
+inst, pk, qap, td = build_problem(ctx, args.workload, args.witness)
+ctx.load_r1cs(inst.nc, inst.ni, inst.m, inst.matrices.row_ptr, inst.matrices.col, inst.matrices.val, inst.matrices.encoding)
+ctx.load_pk(pk.arrays, pk.encoding, 0, 1, bool(args.precompute))
+r_m, s_m = g.fr_to_mont([12345])[0], g.fr_to_mont([67890])[0]
+ctx.upload_witness(inst.z_mont)
+ctx.set_option("serialize", args.serialize)
+ctx.set_option("kernel_events", 1)
+for _ in range(2):
+    ctx.prove_resident(r_m, s_m)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+for _ in range(args.reps):
+    ctx.prove_resident(r_m, s_m)
+    print(json.dumps(ctx.timings()))
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
