@@ -294,7 +294,14 @@ int g16_msm_run_dev(g16_ctx* ctx, int slot, const void* scalars_dev, size_t n, u
     Guard g(ctx);
     MsmBases* mb = &ctx->slot[slot];
     if (mb->group == 0) return set_err(ctx, G16_ERR_BAD_ARG, "msm slot %d has no bases", slot);
-    G16_TRY(msm_run(ctx, mb, &ctx->slot_scratch[slot], (const Fr*)scalars_dev, n, ctx->main));
+    G16_TRY(msm_run(ctx, mb, &ctx->slot_scratch[slot], (const Fr*)scalars_dev, n, ctx->main,
+                    ctx->opt_kernel_events ? ctx->ev_acc[0] : nullptr, ctx->opt_kernel_events ? ctx->ev_acc[1] : nullptr));
+    if (ctx->opt_kernel_events) {
+        G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+        float ms = -1;
+        if (cudaEventElapsedTime(&ms, ctx->ev_acc[0], ctx->ev_acc[1]) != cudaSuccess) cudaGetLastError();
+        ctx->tm.acc_ms[0] = ms;
+    }
     if (out) return xyzz_to_affine_host(ctx, mb->group, ctx->slot_scratch[slot].result, out, out_inf, ctx->main);
     return G16_OK;
 }
@@ -720,6 +727,7 @@ int g16_set_option(g16_ctx* ctx, const char* key, int value) {
     if (!strcmp(key, "serialize")) ctx->opt_serialize = value;
     else if (!strcmp(key, "kernel_events")) ctx->opt_kernel_events = value;
     else if (!strcmp(key, "window_bits")) ctx->opt_window_bits = value;
+    else if (!strcmp(key, "acc_variant")) ctx->opt_acc_variant = value;
     else return set_err(ctx, G16_ERR_BAD_ARG, "unknown option '%s'", key);
     return G16_OK;
 }

@@ -380,15 +380,17 @@ struct Fq2 {
     friend G16_HD Fq2 operator-(const Fq2& a, const Fq2& b) { return Fq2{a.c0 - b.c0, a.c1 - b.c1}; }
     G16_HD Fq2 neg() const { return Fq2{c0.neg(), c1.neg()}; }
     G16_HD Fq2 dbl() const { return Fq2{c0.dbl(), c1.dbl()}; }
-    // Karatsuba: 3 Fq multiplications
-    friend G16_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
+    // Karatsuba: 3 Fq multiplications.  Deliberately a real call on the device: with everything inlined the G2 bucket
+    // loop is 28 Fq products (~110 KB of SASS), overflows the instruction cache (ncu: stall_no_instruction second
+    // largest) and needs 255 registers; as calls it runs 12 % faster at 168 registers (profiles/r01_notes.md).
+    friend G16_HD_NOINLINE Fq2 operator*(const Fq2& a, const Fq2& b) {
         Fq v0 = a.c0 * b.c0;
         Fq v1 = a.c1 * b.c1;
         Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
         return Fq2{v0 - v1, s - v0 - v1};
     }
     // complex squaring: 2 Fq multiplications
-    G16_HD Fq2 sqr() const {
+    G16_HD_NOINLINE Fq2 sqr() const {
         Fq t = c0 * c1;
         return Fq2{(c0 + c1) * (c0 - c1), t.dbl()};
     }

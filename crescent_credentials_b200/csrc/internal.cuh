@@ -110,7 +110,7 @@ struct g16_ctx {
     void* d_partial = nullptr;  // g16_partial on the device
     void* d_small = nullptr;    // small device scratch for assembly
     g16_timings tm = {};
-    int opt_serialize = 0, opt_kernel_events = 0, opt_window_bits = 0;
+    int opt_serialize = 0, opt_kernel_events = 0, opt_window_bits = 0, opt_acc_variant = 0;
     cudaEvent_t ev_acc[10] = {};
 
     // generic MSM slots

@@ -344,8 +344,8 @@ __global__ void k_make_tasks(const uint32_t* __restrict__ start, const uint32_t*
 }
 
 // ---- 5. bucket accumulation --------------------------------------------------------------------------------------------------
-template <class F>
-__global__ void __launch_bounds__(128)
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB)
     k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ vals,
                  const uint32_t* __restrict__ order_keys, const uint32_t* __restrict__ order,
                  const uint32_t* __restrict__ t_start, const uint32_t* __restrict__ t_len, XYZZ<F>* __restrict__ partial,
@@ -680,8 +680,18 @@ static int msm_run_t(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scala
         size_t want = (tcap + 127) / 128;
         unsigned grid = (unsigned)(want < (size_t)kNumSMs * 8 ? want : (size_t)kNumSMs * 8);
         if (ev0) G16_CUDA(ctx, cudaEventRecord(ev0, st));
-        G16_LAUNCH(ctx, k_accumulate<F>, grid, 128, 0, st, (const Affine<F>*)mb->pts, vals, tkeys, tvals, t_start, t_len,
-                   (XYZZ<F>*)sc->partial, tcap);
+        const int variant = ctx->opt_acc_variant;
+#define G16_ACC(MINB)                                                                                                        \
+    G16_LAUNCH(ctx, (k_accumulate<F, MINB>), grid, 128, 0, st, (const Affine<F>*)mb->pts, vals, tkeys, tvals, t_start, t_len, \
+               (XYZZ<F>*)sc->partial, tcap)
+        if constexpr (sizeof(F) == sizeof(Fq)) {
+            if (variant == 4) G16_ACC(4);
+            else G16_ACC(3);  // 148 registers, no spills; occupancy beyond 3 blocks/SM buys nothing (measured)
+        } else {
+            if (variant == 2) G16_ACC(2);
+            else G16_ACC(3);  // 168 registers with out-of-line Fq2 products
+        }
+#undef G16_ACC
         if (ev1) G16_CUDA(ctx, cudaEventRecord(ev1, st));
     }
     // 6. combine task partials per bucket

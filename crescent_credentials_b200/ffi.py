@@ -9,7 +9,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libg16b200.so")
+LIB_PATH = os.environ.get("G16_LIB", os.path.join(_HERE, "libg16b200.so"))  # G16_LIB: kernel-variant experiments
 
 G16_OK = 0
 ERR_DEGREE_TOO_LARGE, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_VANISHING_ZERO = 1, 2, 3, 4, 5, 6

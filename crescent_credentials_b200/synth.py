@@ -65,8 +65,9 @@ def _coeff_table() -> np.ndarray:
     return np.array(rows, dtype=np.uint64)
 
 
-def _matrix(seed: int, tag: int, nc: int, m: int, mean: float, min_len: int, col_lo: int):
-    """Returns row_ptr, col, val (canonical) of one random sparse matrix."""
+def _matrix(seed: int, tag: int, nc: int, m: int, mean: float, min_len: int, col_lo: int, absent_pct: int = 0):
+    """Returns row_ptr, col, val (canonical) of one random sparse matrix.  absent_pct > 0 keeps that share of the wires
+    out of the matrix altogether (w % 20 < absent_pct / 5), which is what makes b_g1 / b_g2 query points infinity."""
     u = (stream(seed, tag, nc) >> np.uint64(11)).astype(np.float64) / float(1 << 53)
     p = 1.0 / mean
     lens = np.floor(np.log(np.maximum(u, 1e-300)) / np.log(1.0 - p)).astype(np.int64) + min_len
@@ -79,6 +80,11 @@ def _matrix(seed: int, tag: int, nc: int, m: int, mean: float, min_len: int, col
     span = np.uint64(m - col_lo)
     hot = np.uint64(min(1 << 16, m - col_lo))
     col = np.where((sel % np.uint64(10)) < np.uint64(3), pick % hot, pick % span).astype(np.uint32) + np.uint32(col_lo)
+    if absent_pct:
+        skip = absent_pct // 5                      # wires with (w % 20) < skip never occur
+        keep = 20 - skip
+        k = (col.astype(np.int64) * keep) // 20     # uniform over the kept wires, same hot/cold shape
+        col = np.minimum(20 * (k // keep) + skip + (k % keep), m - 1).astype(np.uint32)
     kind = (sel >> np.uint64(8)) % np.uint64(10)
     sign = ((sel >> np.uint64(16)) & np.uint64(1)).astype(np.int64)
     k = ((sel >> np.uint64(20)) % np.uint64(121)).astype(np.int64)
@@ -125,7 +131,7 @@ def make_instance(ctx: ffi.Context, name: str, seed: int = 0xC0FFEE, witness: st
     cfg.update(override)
     nc, ni, m, mean = cfg["nc"], cfg["ni"], cfg["m"], cfg["mean"]
     A = _matrix(seed, 0x10, nc, m, mean[0], 1, 0)
-    B = _matrix(seed, 0x20, nc, m, mean[1], 1, 0)
+    B = _matrix(seed, 0x20, nc, m, mean[1], 1, 0, absent_pct=35)  # 35 % of the wires absent from B
     Cr = _matrix(seed, 0x30, nc, m, mean[2], 0, 1)  # columns >= 1: wire 0 is reserved for the solved term
     z = ctx.field_op(ffi.FIELD_FR, ffi.OP_TO_MONT, witness_canonical(seed, m, witness))
     # solve k0 on the GPU with the library's own sparse evaluation

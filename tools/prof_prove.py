@@ -22,7 +22,9 @@ ap.add_argument("--window-bits", type=int, default=0)
 ap.add_argument("--serialize", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
-ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream)
+tstream = torch.cuda.Stream()
+torch.cuda.set_stream(tstream)
+ctx = ffi.Context(0, tstream.cuda_stream)
 if args.window_bits:
     ctx.set_option("window_bits", args.window_bits)
 inst, pk, qap, td = build_problem(ctx, args.workload, args.witness)
