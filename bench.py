@@ -205,6 +205,8 @@ def main():
     def step_resident():
         if world == 1:
             return ctx.prove_resident(r_m, s_m)
+        if rank == 0:
+            ctx.prove_prepare(r_m, s_m)
         ctx.prove_shard_dev()
         ctx.copy_partial_dev(my_part.data_ptr())
         dist.all_gather_into_tensor(gather_buf.view(-1), my_part)

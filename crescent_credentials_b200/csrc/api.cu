@@ -703,8 +703,28 @@ int g16_prove_combine_dev(g16_ctx* ctx, const void* dev_partials, int count, con
     if (!ctx || !dev_partials || !r || !s || !out || count < 1) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "prove_combine: bad argument") : G16_ERR_BAD_ARG;
     Guard g(ctx);
     if (!ctx->have_pk) return set_err(ctx, G16_ERR_BAD_ARG, "prove_combine: no proving key loaded");
-    G16_TRY(assemble_pre(ctx, r, s, ctx->main));
+    if (ctx->pre_pending && !memcmp(ctx->pre_r, r, 32) && !memcmp(ctx->pre_s, s, 32)) {
+        // g16_prove_prepare already ran the (r, s)-only scalar multiplications on a side stream: just join it
+        G16_CUDA(ctx, cudaStreamWaitEvent(ctx->main, ctx->ev_join[4], 0));
+    } else {
+        G16_TRY(assemble_pre(ctx, r, s, ctx->main));
+    }
+    ctx->pre_pending = false;
     return assemble_proof(ctx, dev_partials, count, r, s, out, ctx->main);
+}
+
+int g16_prove_prepare(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4]) {
+    if (!ctx || !r || !s) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!ctx->have_pk) return set_err(ctx, G16_ERR_BAD_ARG, "prove_prepare: no proving key loaded");
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->main));
+    G16_CUDA(ctx, cudaStreamWaitEvent(ctx->side[4], ctx->ev_fork, 0));
+    G16_TRY(assemble_pre(ctx, r, s, ctx->side[4]));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[4], ctx->side[4]));
+    memcpy(ctx->pre_r, r, 32);
+    memcpy(ctx->pre_s, s, 32);
+    ctx->pre_pending = true;
+    return G16_OK;
 }
 
 int g16_prove_combine(g16_ctx* ctx, const g16_partial* partials, int count, const uint64_t r[4], const uint64_t s[4],

@@ -188,6 +188,51 @@ G16_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     return bw;
 }
 
+// e0 += sh[1] (carry into the next limb); sh = sh >> 64 with that carry added at limb 0; sh[6] = sh[7] = 0.
+// The accumulator shift of the stand-alone Montgomery reduction (no product row rides on it).
+G16_HD void lanes_fold_shift(uint32_t& e0, uint32_t* sh) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "addc.cc.u32 %1, %3, 0;\n\t"
+        "addc.cc.u32 %2, %4, 0;\n\t"
+        "addc.cc.u32 %3, %5, 0;\n\t"
+        "addc.cc.u32 %4, %6, 0;\n\t"
+        "addc.cc.u32 %5, %7, 0;\n\t"
+        "addc.u32 %6, %8, 0;"
+        : "+r"(e0), "+r"(sh[0]), "+r"(sh[1]), "+r"(sh[2]), "+r"(sh[3]), "+r"(sh[4]), "+r"(sh[5])
+        : "r"(sh[6]), "r"(sh[7]));
+#else
+    uint64_t t = (uint64_t)e0 + sh[1];
+    e0 = (uint32_t)t;
+    uint64_t c = t >> 32;
+    for (int k = 0; k < 6; k++) {
+        uint64_t v = (uint64_t)sh[k + 2] + c;
+        sh[k] = (uint32_t)v;
+        c = v >> 32;
+    }
+#endif
+    sh[6] = 0;
+    sh[7] = 0;
+}
+
+// lo += x with the carry going into hi (hi cannot overflow in the callers)
+G16_HD void add_carry_into(uint32_t& lo, uint32_t& hi, uint32_t x) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "addc.u32 %1, %1, 0;"
+        : "+r"(lo), "+r"(hi)
+        : "r"(x));
+#else
+    uint64_t t = (uint64_t)lo + x;
+    lo = (uint32_t)t;
+    hi += (uint32_t)(t >> 32);
+#endif
+}
+
+}  // namespace g16
+#include "fp_wide.cuh"
+namespace g16 {
+
 // ---------------------------------------------------------------------------------------------
 // Field parameters.  P = modulus limbs, INV = -p^-1 mod 2^32, R1 = 2^256 mod p (Montgomery one),
 // R2 = 2^512 mod p.  Values: SURVEY appendix, re-derived by oracle/pyref.py in tests/test_constants.py.
@@ -302,8 +347,8 @@ struct alignas(16) Fp {
     }
     G16_HD Fp dbl() const { return *this + *this; }
 
-    // Montgomery product a*b*2^-256 mod p
-    friend G16_HD Fp operator*(const Fp& a, const Fp& b) {
+    // Montgomery product a*b*2^-256 mod p, word-serial CIOS (128 wide multiplies); kept as the reference formulation
+    static G16_HD Fp mul_cios(const Fp& a, const Fp& b) {
         uint32_t X[8], Y[8];  // the two accumulators; their even/odd roles alternate every row
         uint32_t m, cy;
         // row 0
@@ -334,6 +379,61 @@ struct alignas(16) Fp {
         cy = add8(r.v, sh, X);
         reduce_once(r.v, cy);
         return r;
+    }
+    // Montgomery reduction of a 16-limb value P < p * 2^256:  P * 2^-256 mod p, fully reduced.
+    // Same two-accumulator scheme as mul_cios with the product rows removed: the high limbs of P enter one per round
+    // at the top of the accumulator.
+    static G16_HD Fp reduce_wide(const uint32_t* P) {
+        uint32_t X[8], Y[8];
+        uint32_t m, cy;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            X[k] = P[k];
+            Y[k] = 0;
+        }
+        m = X[0] * PR::INV;
+        lanes_mad(Y, PR::P(1), PR::P(3), PR::P(5), PR::P(7), m);
+        cy = lanes_mad(X, PR::P(0), PR::P(2), PR::P(4), PR::P(6), m);
+        Y[7] += cy;
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            uint32_t* ev = (i & 1) ? Y : X;
+            uint32_t* od = (i & 1) ? X : Y;
+            lanes_fold_shift(ev[0], od);
+            add_carry_into(ev[7], od[7], P[7 + i]);
+            m = ev[0] * PR::INV;
+            lanes_mad(od, PR::P(1), PR::P(3), PR::P(5), PR::P(7), m);
+            cy = lanes_mad(ev, PR::P(0), PR::P(2), PR::P(4), PR::P(6), m);
+            od[7] += cy;
+        }
+        Fp r;
+        uint32_t sh[8];
+#pragma unroll
+        for (int k = 0; k < 7; k++) sh[k] = Y[k + 1];
+        sh[7] = P[15];
+        cy = add8(r.v, sh, X);
+        reduce_once(r.v, cy);
+        return r;
+    }
+
+    // Montgomery product.  Default: word-serial CIOS (123 IMAD.WIDE + 8 IMAD.HI + 9 IMAD + 39 IADD3 in SASS).
+    // G16_MUL_KARATSUBA selects the 16-limb Karatsuba product + separate reduction (103 IMAD.WIDE + 15 IMAD.HI but
+    // 132 IADD3 + 44 SEL/LOP3): measured SLOWER on B200 (56.2 vs 64.9 G mul/s, bucket loop 8.5 vs 6.3 ms) because the
+    // extra ALU work and code size cost more than the 10 % of wide multiplies they save.  Kept for the record and
+    // because reduce_wide is the building block for sharing reductions between products.
+    friend G16_HD Fp operator*(const Fp& a, const Fp& b) {
+#ifdef G16_MUL_KARATSUBA
+        uint32_t P[16];
+        mul8_wide(P, a.v, b.v);
+        return reduce_wide(P);
+#else
+        return mul_cios(a, b);
+#endif
+    }
+    static G16_HD Fp mul_karatsuba(const Fp& a, const Fp& b) {
+        uint32_t P[16];
+        mul8_wide(P, a.v, b.v);
+        return reduce_wide(P);
     }
     G16_HD Fp sqr() const { return (*this) * (*this); }
 

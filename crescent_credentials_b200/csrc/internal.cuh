@@ -112,6 +112,8 @@ struct g16_ctx {
     g16_timings tm = {};
     int opt_serialize = 0, opt_kernel_events = 0, opt_window_bits = 0, opt_acc_variant = 0;
     cudaEvent_t ev_acc[10] = {};
+    bool pre_pending = false;  // k_assemble_pre already in flight for (pre_r, pre_s)
+    uint64_t pre_r[4] = {}, pre_s[4] = {};
 
     // generic MSM slots
     g16::MsmBases slot[g16::kMsmSlots];

@@ -163,64 +163,71 @@ static int exclusive_scan(g16_ctx* ctx, uint32_t* data, size_t n, uint32_t* tmp,
     return G16_OK;
 }
 
-// ---- LSD radix sort of (key, value) pairs, 8 bits per pass, segmented ----------------------------------------------------
+// ---- LSD radix sort of (key, value) pairs, 8..11 bits per pass, segmented ------------------------------------------------
 // hist layout: [segment][bin][tile]  (flat exclusive scan => absolute output positions, segments stay separate
-// because every segment holds exactly seg_len items).
+// because every segment holds exactly seg_len items).  Wide digits keep the pass count at 2 for 20-bit bucket keys.
+constexpr unsigned kRsMaxBits = 11;
+
+template <unsigned BITS>
 __global__ void __launch_bounds__(kRsThreads)
     k_rs_hist(const uint32_t* __restrict__ keys, size_t seg_len, unsigned tiles_per_seg, unsigned shift,
               uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sh[256];
+    constexpr unsigned NB = 1u << BITS;
+    __shared__ uint32_t sh[NB];
     unsigned seg = blockIdx.x / tiles_per_seg, tile = blockIdx.x % tiles_per_seg;
-    sh[threadIdx.x] = 0;
+    for (unsigned b = threadIdx.x; b < NB; b += kRsThreads) sh[b] = 0;
     __syncthreads();
     size_t seg_base = (size_t)seg * seg_len;
     size_t lo = (size_t)tile * kRsTile;
 #pragma unroll
     for (int k = 0; k < kRsItems; k++) {
         size_t i = lo + (size_t)k * kRsThreads + threadIdx.x;
-        if (i < seg_len) atomicAdd(&sh[(keys[seg_base + i] >> shift) & 0xffu], 1u);
+        if (i < seg_len) atomicAdd(&sh[(keys[seg_base + i] >> shift) & (NB - 1)], 1u);
     }
     __syncthreads();
-    hist[((size_t)seg * 256 + threadIdx.x) * tiles_per_seg + tile] = sh[threadIdx.x];
+    for (unsigned b = threadIdx.x; b < NB; b += kRsThreads) hist[((size_t)seg * NB + b) * tiles_per_seg + tile] = sh[b];
 }
 
+template <unsigned BITS>
 __global__ void __launch_bounds__(kRsThreads)
     k_rs_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t* __restrict__ okeys,
                  uint32_t* __restrict__ ovals, size_t seg_len, unsigned tiles_per_seg, unsigned shift,
                  const uint32_t* __restrict__ hist) {
-    __shared__ uint32_t wcnt[kRsThreads / 32][256];
+    constexpr unsigned NB = 1u << BITS;
+    constexpr unsigned NW = kRsThreads / 32;
+    extern __shared__ uint32_t wcnt[];  // [NW][NB]
     unsigned seg = blockIdx.x / tiles_per_seg, tile = blockIdx.x % tiles_per_seg;
     unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (unsigned i = threadIdx.x; i < (kRsThreads / 32) * 256; i += kRsThreads) (&wcnt[0][0])[i] = 0;
+    for (unsigned i = threadIdx.x; i < NW * NB; i += kRsThreads) wcnt[i] = 0;
     __syncthreads();
+    uint32_t* mine = wcnt + wid * NB;
     size_t seg_base = (size_t)seg * seg_len;
     // warp w owns items [w*512, (w+1)*512) of the tile, as 16 rows of 32: ranking order == index order (stable)
     size_t lo = (size_t)tile * kRsTile + (size_t)wid * (32 * kRsItems);
     uint32_t k[kRsItems], v[kRsItems];
-    uint32_t packed[kRsItems];  // rank within row-group (low 8 bits... up to 32) | group size << 8 | leader flag << 16
+    uint32_t packed[kRsItems];  // rank within the row's digit group | group size << 8 | leader << 16 | valid << 17
 #pragma unroll
     for (int r = 0; r < kRsItems; r++) {
         size_t i = lo + (size_t)r * 32 + lane;
         bool valid = i < seg_len;
         k[r] = valid ? keys[seg_base + i] : 0xffffffffu;
         v[r] = valid ? vals[seg_base + i] : 0u;
-        uint32_t d = valid ? ((k[r] >> shift) & 0xffu) : (0x100u + lane);
+        uint32_t d = valid ? ((k[r] >> shift) & (NB - 1)) : (NB + lane);
         uint32_t mask = __match_any_sync(0xffffffffu, d);
         uint32_t rank = __popc(mask & ((1u << lane) - 1u));
         uint32_t cnt = __popc(mask);
         bool leader = rank == 0;
         packed[r] = rank | (cnt << 8) | ((leader && valid) ? 0x10000u : 0u) | (valid ? 0x20000u : 0u);
-        if (leader && valid) wcnt[wid][d] += cnt;
+        if (leader && valid) mine[d] += cnt;
         __syncwarp();
     }
     __syncthreads();
-    {
-        unsigned bin = threadIdx.x;
-        uint32_t run = hist[((size_t)seg * 256 + bin) * tiles_per_seg + tile];
+    for (unsigned bin = threadIdx.x; bin < NB; bin += kRsThreads) {
+        uint32_t run = hist[((size_t)seg * NB + bin) * tiles_per_seg + tile];
 #pragma unroll
-        for (int w = 0; w < kRsThreads / 32; w++) {
-            uint32_t t = wcnt[w][bin];
-            wcnt[w][bin] = run;
+        for (unsigned w = 0; w < NW; w++) {
+            uint32_t t = wcnt[w * NB + bin];
+            wcnt[w * NB + bin] = run;
             run += t;
         }
     }
@@ -228,11 +235,11 @@ __global__ void __launch_bounds__(kRsThreads)
 #pragma unroll
     for (int r = 0; r < kRsItems; r++) {
         bool valid = (packed[r] & 0x20000u) != 0;
-        uint32_t d = (k[r] >> shift) & 0xffu;
+        uint32_t d = (k[r] >> shift) & (NB - 1);
         uint32_t pos = 0;
-        if (valid) pos = wcnt[wid][d] + (packed[r] & 0xffu);
+        if (valid) pos = mine[d] + (packed[r] & 0xffu);
         __syncwarp();
-        if (packed[r] & 0x10000u) wcnt[wid][d] += (packed[r] >> 8) & 0xffu;
+        if (packed[r] & 0x10000u) mine[d] += (packed[r] >> 8) & 0xffu;
         __syncwarp();
         if (valid) {
             okeys[pos] = k[r];
@@ -241,17 +248,43 @@ __global__ void __launch_bounds__(kRsThreads)
     }
 }
 
+template <unsigned BITS>
+static int radix_pass(g16_ctx* ctx, const uint32_t* keys, const uint32_t* vals, uint32_t* okeys, uint32_t* ovals, size_t seg_len,
+                      unsigned nseg, unsigned tiles, unsigned shift, uint32_t* hist, uint32_t* scan_tmp, cudaStream_t st) {
+    constexpr unsigned NB = 1u << BITS;
+    const size_t smem = (size_t)(kRsThreads / 32) * NB * sizeof(uint32_t);
+    static bool attr_done = false;
+    if (!attr_done && smem > 48 * 1024) {
+        G16_CUDA(ctx, cudaFuncSetAttribute(k_rs_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    G16_LAUNCH(ctx, k_rs_hist<BITS>, nseg * tiles, kRsThreads, 0, st, keys, seg_len, tiles, shift, hist);
+    G16_TRY(exclusive_scan(ctx, hist, (size_t)nseg * NB * tiles, scan_tmp, nullptr, st));
+    G16_LAUNCH(ctx, k_rs_scatter<BITS>, nseg * tiles, kRsThreads, smem, st, keys, vals, okeys, ovals, seg_len, tiles, shift, hist);
+    return G16_OK;
+}
+
+static unsigned radix_digit_bits(unsigned bits) {
+    unsigned passes = (bits + kRsMaxBits - 1) / kRsMaxBits;
+    unsigned per = (bits + passes - 1) / passes;
+    return per < 8 ? 8 : per;
+}
+
 // sorts nseg segments of seg_len pairs by the low `bits` key bits; result ends in (*keys, *vals) (buffers may swap)
 static int radix_sort(g16_ctx* ctx, uint32_t** keys, uint32_t** vals, uint32_t** keys_alt, uint32_t** vals_alt,
                       size_t seg_len, unsigned nseg, unsigned bits, uint32_t* hist, uint32_t* scan_tmp, cudaStream_t st) {
     if (seg_len == 0 || nseg == 0) return G16_OK;
     unsigned tiles = (unsigned)((seg_len + kRsTile - 1) / kRsTile);
-    size_t hist_n = (size_t)nseg * 256 * tiles;
-    for (unsigned shift = 0; shift < bits; shift += 8) {
-        G16_LAUNCH(ctx, k_rs_hist, nseg * tiles, kRsThreads, 0, st, *keys, seg_len, tiles, shift, hist);
-        G16_TRY(exclusive_scan(ctx, hist, hist_n, scan_tmp, nullptr, st));
-        G16_LAUNCH(ctx, k_rs_scatter, nseg * tiles, kRsThreads, 0, st, *keys, *vals, *keys_alt, *vals_alt, seg_len, tiles,
-                   shift, hist);
+    unsigned per = radix_digit_bits(bits);
+    for (unsigned shift = 0; shift < bits; shift += per) {
+        int rc;
+        switch (per) {
+            case 8: rc = radix_pass<8>(ctx, *keys, *vals, *keys_alt, *vals_alt, seg_len, nseg, tiles, shift, hist, scan_tmp, st); break;
+            case 9: rc = radix_pass<9>(ctx, *keys, *vals, *keys_alt, *vals_alt, seg_len, nseg, tiles, shift, hist, scan_tmp, st); break;
+            case 10: rc = radix_pass<10>(ctx, *keys, *vals, *keys_alt, *vals_alt, seg_len, nseg, tiles, shift, hist, scan_tmp, st); break;
+            default: rc = radix_pass<11>(ctx, *keys, *vals, *keys_alt, *vals_alt, seg_len, nseg, tiles, shift, hist, scan_tmp, st); break;
+        }
+        G16_TRY(rc);
         std::swap(*keys, *keys_alt);
         std::swap(*vals, *vals_alt);
     }
@@ -538,9 +571,9 @@ static int msm_alloc_scratch(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc) {
     size_t sort_n = items > tcap ? items : tcap;
     size_t seg_len = mb->precomp ? items : n;
     size_t tiles = (seg_len + kRsTile - 1) / kRsTile;
-    size_t hist_n = (size_t)nseg * 256 * tiles;
+    size_t hist_n = (size_t)nseg * (1u << kRsMaxBits) * tiles;
     size_t ttiles = (tcap + kRsTile - 1) / kRsTile;
-    if (256 * ttiles > hist_n) hist_n = 256 * ttiles;
+    if ((size_t)(1u << kRsMaxBits) * ttiles > hist_n) hist_n = (size_t)(1u << kRsMaxBits) * ttiles;
     sc->cap_items = items;
     sc->cap_buckets = nbuckets;
     sc->cap_tasks = tcap;
@@ -554,7 +587,7 @@ static int msm_alloc_scratch(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc) {
     G16_TRY(dev_alloc(ctx, &sc->task_off, nbuckets + 1));
     size_t scan_tmp = (hist_n > nbuckets ? hist_n : nbuckets) / kScanTile + 2;
     G16_TRY(dev_alloc(ctx, &sc->task_tmp, scan_tmp));
-    G16_TRY(dev_alloc(ctx, &sc->tasks, 2 * tcap));  // t_start | t_len
+    G16_TRY(dev_alloc(ctx, &sc->tasks, 4 * tcap));  // t_start | t_len | task-sort alternates (keys, order)
     G16_TRY(dev_alloc(ctx, &sc->counters, 16));
     size_t chunks = (size_t)nseg * ((nb + kChunk - 1) / kChunk);
     XYZZ<F>* p;
@@ -664,16 +697,13 @@ static int msm_run_t(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scala
     uint32_t* t_len = sc->tasks + tcap;
     G16_LAUNCH(ctx, k_make_tasks, (unsigned)((nbuckets + 255) / 256), 256, 0, st, sc->bucket_start, sc->task_off, nseg, nb,
                tkeys, tvals, t_start, t_len);
-    // task sort needs its own alternate buffers: reuse the tail of the (now dead) key array of the pair sort
-    // keys/vals (sorted pairs) must stay intact: vals is read by k_accumulate; keys is dead after k_bucket_bounds.
-    uint32_t* tk_alt = keys;                    // dead after step 3
-    uint32_t* tv_alt = (uint32_t*)sc->partial;  // partial buffer is written only by k_accumulate, later
+    uint32_t* tk_alt = sc->tasks + 2 * tcap;  // dedicated: with one 9-bit pass the sorted order ENDS in the alternates,
+    uint32_t* tv_alt = sc->tasks + 3 * tcap;  // which k_accumulate reads while it writes sc->partial
     {
         uint32_t *a = tkeys, *b = tvals, *a2 = tk_alt, *b2 = tv_alt;
         G16_TRY(radix_sort(ctx, &a, &b, &a2, &b2, tcap, 1, 9, sc->hist, sc->task_tmp, st));
         tkeys = a;
         tvals = b;
-        // two 8-bit passes: results are back in the original buffers (even number of swaps)
     }
     // 5. accumulate
     {

@@ -28,7 +28,7 @@ EXPORTS = [
     "g16_msm_run_dev", "g16_ntt", "g16_ntt_dev", "g16_field_op", "g16_fixed_base_g1", "g16_fixed_base_g2",
     "g16_fixed_base_g1_dev", "g16_fixed_base_g2_dev", "g16_r1cs_eval", "g16_dev_alloc", "g16_dev_free",
     "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count", "g16_set_option",
-    "g16_pow_table", "g16_copy_partial_dev",
+    "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare",
 ]
 
 _u64p = C.POINTER(C.c_uint64)
@@ -114,6 +114,7 @@ def load_library() -> C.CDLL:
     lib.g16_partial_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.g16_prove_shard_dev.argtypes = [C.c_void_p, C.c_int]
     lib.g16_copy_partial_dev.argtypes = [C.c_void_p, C.c_void_p]
+    lib.g16_prove_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.g16_prove_combine_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
     lib.g16_witness_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.g16_domain_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
@@ -341,6 +342,11 @@ class Context:
 
     def prove_shard_dev(self, reduction=REDUCTION_LIBSNARK):
         self.check(self.lib.g16_prove_shard_dev(self.h, reduction))
+
+    def prove_prepare(self, r, s):
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        self.check(self.lib.g16_prove_prepare(self.h, _ptr(r), _ptr(s)))
 
     def copy_partial_dev(self, dst_dev: int):
         self.check(self.lib.g16_copy_partial_dev(self.h, C.c_void_p(dst_dev)))

@@ -44,13 +44,15 @@ class ShardedProver:
 
     def prove(self, z_mont, r: int, s: int, reduction=ffi.REDUCTION_LIBSNARK) -> Optional[Proof]:
         """z_mont: (m, 4) uint64 Montgomery witness (same on every rank).  Returns the proof on rank 0, None elsewhere."""
+        rr, ss = fr_to_mont([r % R_MOD])[0], fr_to_mont([s % R_MOD])[0]
         self.ctx.upload_witness(z_mont)
+        if self.rank == 0:
+            self.ctx.prove_prepare(rr, ss)   # overlaps r*delta, s*delta, ... with the shard MSMs
         self.ctx.prove_shard_dev(reduction)
         self.ctx.copy_partial_dev(self.mine.data_ptr())
         allp = gather_partials(self.mine, self.world)
         if self.rank != 0:
             return None
-        rr, ss = fr_to_mont([r % R_MOD])[0], fr_to_mont([s % R_MOD])[0]
         return Proof.from_ffi(self.ctx.prove_combine_dev(allp.data_ptr(), self.world, rr, ss))
 
     def close(self):

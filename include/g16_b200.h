@@ -153,6 +153,9 @@ int g16_prove_combine(g16_ctx* ctx, const g16_partial* partials, int count, cons
 int g16_partial_dev(g16_ctx* ctx, void** dev_ptr, size_t* bytes);
 int g16_prove_shard_dev(g16_ctx* ctx, int reduction);          /* witness resident; result left in the device partial */
 int g16_copy_partial_dev(g16_ctx* ctx, void* dst_dev);         /* stream-ordered D2D copy of the partial (e.g. into an NCCL buffer) */
+/* Optional, rank 0: starts the (r, s, pk)-only scalar multiplications on a side stream so that they overlap the shard work;
+ * a later g16_prove_combine[_dev] with the same (r, s) joins them instead of running them serially. */
+int g16_prove_prepare(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4]);
 int g16_prove_combine_dev(g16_ctx* ctx, const void* dev_partials, int count, const uint64_t r[4], const uint64_t s[4],
                           g16_proof* out);
 

@@ -16,6 +16,7 @@ template <class F> static void bin(int op, const uint32_t* a, const uint32_t* b,
         case 5: z = x.to_mont(); break;
         case 6: z = x.from_mont(); break;
         case 7: z = x.sqr(); break;
+        case 8: z = F::mul_karatsuba(x, y); break;
         default: z = F::zero();
     }
     memcpy(r, z.v, 32);

@@ -80,6 +80,7 @@ def test_device_montgomery_code_on_host_matches_oracle(host_fp, name, p):
         others = edge if k < len(edge) else [vals[(k * 7 + 3) % len(vals)]]
         for b in others:
             assert dec(_call(fn, 0, le(a), le(b))) == a * b * rinv % p
+            assert dec(_call(fn, 8, le(a), le(b))) == a * b * rinv % p   # Karatsuba + separate reduction variant
             assert dec(_call(fn, 1, le(a), le(b))) == (a + b) % p
             assert dec(_call(fn, 2, le(a), le(b))) == (a - b) % p
         assert dec(_call(fn, 3, le(a), le(0))) == (-a) % p
