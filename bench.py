@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--witness", default="uniform", choices=["uniform", "circom"])
     ap.add_argument("--precompute", type=int, default=1)
     ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--ba-levels", type=int, default=-1, help="batched-affine levels before the XYZZ tail (-1 = library default)")
+    ap.add_argument("--share-digits", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     args = ap.parse_args()
@@ -192,6 +194,8 @@ def main():
         ctx.set_option("window_bits", args.window_bits)
     inst, pk, qap, td = build_problem(ctx, args.workload, args.witness)
     ctx.load_r1cs(inst.nc, inst.ni, inst.m, inst.matrices.row_ptr, inst.matrices.col, inst.matrices.val, inst.matrices.encoding)
+    ctx.set_option("ba_levels", args.ba_levels)
+    ctx.set_option("share_digits", args.share_digits)
     ctx.load_pk(pk.arrays, pk.encoding, rank, world, bool(args.precompute))
 
     # pinned host witness for the end-to-end path

@@ -511,13 +511,51 @@ int g16_ctx_load_pk(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int sha
     size_t lo, hi;
     range(pk->h_len, &lo, &hi);
     G16_TRY(load_query(ctx, Q_H, 1, pk->h_query, pk->h_len, lo, hi, enc, precompute));
-    range(pk->l_len, &lo, &hi);
-    G16_TRY(load_query(ctx, Q_L, 1, pk->l_query, pk->l_len, lo, hi, enc, precompute));
     size_t m1 = pk->a_len - 1;  // MSM over query[1..] (prover.rs:266)
     range(m1, &lo, &hi);
     G16_TRY(load_query(ctx, Q_A, 1, pk->a_query + 8, m1, lo, hi, enc, precompute));
     G16_TRY(load_query(ctx, Q_B1, 1, pk->b_g1_query + 8, m1, lo, hi, enc, precompute));
     G16_TRY(load_query(ctx, Q_B2, 2, pk->b_g2_query + 16, m1, lo, hi, enc, precompute));
+    // b_g1 and b_g2 run over the same scalars z[1..] and are at infinity for the same wires (those absent from B): one
+    // digit stage (scalar recoding + bucket sort) serves both.
+    ctx->share_b = false;
+    if (ctx->opt_share_digits) G16_TRY(msm_can_share(ctx, &ctx->q[Q_B1], &ctx->q[Q_B2], (hi - lo) / 64, &ctx->share_b, ctx->main));
+    // l runs over aux = z[num_instance..], a over z[1..]: laying l_query out on a's index space (num_instance - 1 leading
+    // points at infinity) lets l reuse a's digit stage.  Only worth it when a_query has (almost) no infinity points of its
+    // own, because a's skipped wires would otherwise be idle lanes in l's additions -- decided here, per key.
+    ctx->share_al = false;
+    // l's shard always follows a's (the ranks' l ranges must partition l_query whatever each rank decides about sharing)
+    size_t l_lo, l_hi;
+    const bool aligned = pk->l_len <= m1;
+    const size_t shift = aligned ? m1 - pk->l_len : 0;  // = num_instance - 1
+    if (aligned) {
+        l_lo = (lo > shift ? lo : shift) - shift;
+        l_hi = (hi > shift ? hi : shift) - shift;
+    } else {
+        range(pk->l_len, &l_lo, &l_hi);
+    }
+    if (ctx->opt_share_digits && aligned && hi > lo) {
+        size_t cnt = hi - lo;
+        void* stage = nullptr;
+        G16_CUDA(ctx, cudaMalloc(&stage, cnt * 64));
+        int rc = G16_OK;
+        cudaError_t e = cudaMemsetAsync(stage, 0, cnt * 64, ctx->main);
+        if (e == cudaSuccess && l_hi > l_lo)
+            e = cudaMemcpyAsync((char*)stage + (l_lo + shift - lo) * 64, (const char*)pk->l_query + l_lo * 64, (l_hi - l_lo) * 64,
+                                cudaMemcpyHostToDevice, ctx->main);
+        if (e != cudaSuccess) rc = set_err(ctx, G16_ERR_CUDA, "pk upload: %s", cudaGetErrorString(e));
+        if (rc == G16_OK && enc == G16_ENC_CANONICAL) rc = convert_mont_dev(ctx, G16_FIELD_FQ, stage, cnt * 2, true, ctx->main);
+        if (rc == G16_OK)
+            rc = msm_set_bases(ctx, &ctx->q[Q_L], &ctx->scratch[Q_L], 1, stage, cnt, ctx->opt_window_bits, precompute != 0, ctx->main);
+        if (rc == G16_OK) rc = msm_can_share(ctx, &ctx->q[Q_A], &ctx->q[Q_L], shift + cnt / 64, &ctx->share_al, ctx->main);
+        cudaStreamSynchronize(ctx->main);
+        cudaFree(stage);
+        G16_TRY(rc);
+        ctx->pk_len[Q_L] = pk->l_len;
+        ctx->sh_lo[Q_L] = l_lo;
+        ctx->sh_hi[Q_L] = l_hi;
+    }
+    if (!ctx->share_al) G16_TRY(load_query(ctx, Q_L, 1, pk->l_query, pk->l_len, l_lo, l_hi, enc, precompute));
     ctx->have_pk = true;
     return G16_OK;
 }
@@ -547,25 +585,60 @@ static int prove_shard_streams(g16_ctx* ctx, int reduction) {
     cudaStream_t main = ctx->main;
     PartialLayout* part = (PartialLayout*)ctx->d_partial;
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
-    // z-only MSMs on the side streams: l (aux = z[ni..]), a / b_g1 / b_g2 (assignment = z[1..])   (prover.rs:70-74,89-117)
-    const int side_q[4] = {Q_L, Q_A, Q_B1, Q_B2};
-    for (int k = 0; k < 4; k++) {
+    // z-only MSMs on the side streams: l (aux = z[ni..]), a / b_g1 / b_g2 (assignment = z[1..])   (prover.rs:70-74,89-117).
+    // MSMs that share a digit stage run back to back on one stream.
+    struct Job {
+        int qi, from;
+    };
+    Job chains[4][2];
+    int chain_len[4] = {0, 0, 0, 0};
+    int nchains = 0;
+    if (ctx->share_al) {
+        chains[nchains][0] = {Q_A, -1};
+        chains[nchains][1] = {Q_L, Q_A};
+        chain_len[nchains++] = 2;
+    } else {
+        chains[nchains][0] = {Q_L, -1};
+        chain_len[nchains++] = 1;
+        chains[nchains][0] = {Q_A, -1};
+        chain_len[nchains++] = 1;
+    }
+    if (ctx->share_b) {
+        chains[nchains][0] = {Q_B1, -1};
+        chains[nchains][1] = {Q_B2, Q_B1};
+        chain_len[nchains++] = 2;
+    } else {
+        chains[nchains][0] = {Q_B1, -1};
+        chain_len[nchains++] = 1;
+        chains[nchains][0] = {Q_B2, -1};
+        chain_len[nchains++] = 1;
+    }
+    for (int k = 0; k < nchains; k++) {
         cudaStream_t st = ctx->opt_serialize ? main : ctx->side[k];
-        int qi = side_q[k];
-        cudaEvent_t ea0 = ctx->opt_kernel_events ? ctx->ev_acc[2 * qi] : nullptr;
-        cudaEvent_t ea1 = ctx->opt_kernel_events ? ctx->ev_acc[2 * qi + 1] : nullptr;
         if (!ctx->opt_serialize) G16_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
-        const Fr* sc = ctx->d_z + (qi == Q_L ? ctx->ni : 1) + ctx->sh_lo[qi];
-        size_t cnt = ctx->sh_hi[qi] - ctx->sh_lo[qi];
-        G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * qi], st));
-        G16_TRY(msm_run(ctx, &ctx->q[qi], &ctx->scratch[qi], sc, cnt, st, ea0, ea1));
-        void* dst = qi == Q_L ? (void*)&part->l : qi == Q_A ? (void*)&part->a : qi == Q_B1 ? (void*)&part->b1 : (void*)&part->b2;
-        size_t bytes = qi == Q_B2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
-        if (cnt && ctx->scratch[qi].result)
-            G16_CUDA(ctx, cudaMemcpyAsync(dst, ctx->scratch[qi].result, bytes, cudaMemcpyDeviceToDevice, st));
-        else
-            G16_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, st));
-        G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * qi], st));
+        for (int j = 0; j < chain_len[k]; j++) {
+            int qi = chains[k][j].qi, from = chains[k][j].from;
+            cudaEvent_t ea0 = ctx->opt_kernel_events ? ctx->ev_acc[2 * qi] : nullptr;
+            cudaEvent_t ea1 = ctx->opt_kernel_events ? ctx->ev_acc[2 * qi + 1] : nullptr;
+            const Fr* sc;
+            size_t cnt;
+            if (from >= 0) {  // same scalars and index space as the MSM whose digit stage is reused
+                sc = nullptr;
+                cnt = ctx->sh_hi[from] - ctx->sh_lo[from];
+            } else {
+                sc = ctx->d_z + (qi == Q_L ? ctx->ni : 1) + ctx->sh_lo[qi];
+                cnt = ctx->sh_hi[qi] - ctx->sh_lo[qi];
+            }
+            G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * qi], st));
+            G16_TRY(msm_run(ctx, &ctx->q[qi], &ctx->scratch[qi], sc, cnt, st, ea0, ea1, from >= 0 ? &ctx->scratch[from] : nullptr));
+            void* dst = qi == Q_L ? (void*)&part->l : qi == Q_A ? (void*)&part->a : qi == Q_B1 ? (void*)&part->b1 : (void*)&part->b2;
+            size_t bytes = qi == Q_B2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
+            if (cnt && ctx->scratch[qi].result)
+                G16_CUDA(ctx, cudaMemcpyAsync(dst, ctx->scratch[qi].result, bytes, cudaMemcpyDeviceToDevice, st));
+            else
+                G16_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, st));
+            G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * qi], st));
+        }
         if (!ctx->opt_serialize) G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], st));
     }
     // main: witness map, then the h MSM over h[lo..hi)  (prover.rs:63-66; the zip drops h[n-1], generator.rs:178)
@@ -584,7 +657,7 @@ static int prove_shard_streams(g16_ctx* ctx, int reduction) {
         G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * Q_H], main));
     }
     if (!ctx->opt_serialize)
-        for (int k = 0; k < 4; k++) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[k], 0));
+        for (int k = 0; k < nchains; k++) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[k], 0));
     return G16_OK;
 }
 
@@ -748,6 +821,8 @@ int g16_set_option(g16_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "kernel_events")) ctx->opt_kernel_events = value;
     else if (!strcmp(key, "window_bits")) ctx->opt_window_bits = value;
     else if (!strcmp(key, "acc_variant")) ctx->opt_acc_variant = value;
+    else if (!strcmp(key, "ba_levels")) ctx->opt_ba_levels = value;
+    else if (!strcmp(key, "share_digits")) ctx->opt_share_digits = value;
     else return set_err(ctx, G16_ERR_BAD_ARG, "unknown option '%s'", key);
     return G16_OK;
 }

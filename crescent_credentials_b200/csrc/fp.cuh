@@ -251,6 +251,10 @@ struct FrParams {
         constexpr uint32_t t[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
         return t[i];
     }
+    static G16_HD constexpr uint32_t R3(int i) {  // 2^768 mod r
+        constexpr uint32_t t[8] = {0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu, 0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu};
+        return t[i];
+    }
 };
 struct FqParams {
     static G16_HD constexpr uint32_t P(int i) {
@@ -264,6 +268,10 @@ struct FqParams {
     }
     static G16_HD constexpr uint32_t R2(int i) {
         constexpr uint32_t t[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return t[i];
+    }
+    static G16_HD constexpr uint32_t R3(int i) {  // 2^768 mod q
+        constexpr uint32_t t[8] = {0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u};
         return t[i];
     }
 };
@@ -460,6 +468,74 @@ struct alignas(16) Fp {
             }
         }
         return acc;
+    }
+
+    // Same inverse by the binary extended Euclidean algorithm: shifts and subtractions only.  A Montgomery product is a
+    // ~1000-cycle dependent chain for a lone warp, so the 380-product Fermat ladder is ~0.2 ms of pure latency; this loop
+    // runs ~380 iterations of a few carry chains each (~8x less latency).  Used where an inversion sits alone on the
+    // critical path (the shared inversions of the batched-affine bucket accumulation).  inverse of 0 is 0.
+    G16_HD_NOINLINE Fp inverse_bgcd() const {
+        if (is_zero()) return zero();
+        // invariants: x1 * a == u, x2 * a == w (mod p) for the integer a = this->v (i.e. value * R)
+        uint32_t u[8], w[8];
+        Fp x1, x2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            u[i] = v[i];
+            w[i] = PR::P(i);
+            x1.v[i] = (i == 0) ? 1u : 0u;
+            x2.v[i] = 0u;
+        }
+        auto is_one = [](const uint32_t* x) {
+            uint32_t o = x[0] ^ 1u;
+#pragma unroll
+            for (int i = 1; i < 8; i++) o |= x[i];
+            return o == 0;
+        };
+        auto shr1 = [](uint32_t* x) {
+#pragma unroll
+            for (int i = 0; i < 7; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+            x[7] >>= 1;
+        };
+        auto half = [&](Fp& x) {  // x / 2 mod p
+            if (x.v[0] & 1u) {
+                uint32_t p[8], t[8];
+                load_p(p);
+                add8(t, x.v, p);  // < 2^255: no carry out
+#pragma unroll
+                for (int i = 0; i < 8; i++) x.v[i] = t[i];
+            }
+            shr1(x.v);
+        };
+        for (int it = 0; it < 1024; it++) {
+            if (is_one(u) || is_one(w)) break;
+            if ((u[0] & 1u) && (w[0] & 1u)) {
+                uint32_t t[8];
+                uint32_t bw = sub8(t, u, w);
+                if (!bw) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) u[i] = t[i];
+                    x1 = x1 - x2;
+                } else {
+                    sub8(t, w, u);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) w[i] = t[i];
+                    x2 = x2 - x1;
+                }
+            }
+            if (!(u[0] & 1u)) {
+                shr1(u);
+                half(x1);
+            } else {
+                shr1(w);
+                half(x2);
+            }
+        }
+        Fp y = is_one(u) ? x1 : x2;  // (value * R)^-1 as a plain integer = value^-1 * R^-1
+        Fp r3;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r3.v[i] = PR::R3(i);
+        return y * r3;  // * R^3 / R  =>  value^-1 * R
     }
 };
 

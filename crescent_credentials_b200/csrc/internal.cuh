@@ -42,9 +42,11 @@ struct MsmBases {
     void* pts = nullptr;    // device: Affine<Fq> or Affine<Fq2>
     bool owns_pts = true;
     uint8_t* skip = nullptr;  // device: 1 if point i is infinity (b-queries hold many)
+    int ba_levels = 0;      // batched-affine levels run before the XYZZ tail
 };
 
 struct MsmScratch {
+    // -- digit stage: depends on the scalars only, so MSMs over the same scalars and skip pattern share it ----------
     size_t cap_items = 0;    // capacity in (window,point) pairs
     size_t cap_buckets = 0;  // capacity in buckets (sets * nb)
     uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
@@ -53,15 +55,26 @@ struct MsmScratch {
     uint32_t* bucket_start = nullptr;  // sets*(nb+1)
     uint32_t* task_off = nullptr;      // per bucket: first task id (exclusive scan of tasks per bucket), +1
     uint32_t* task_tmp = nullptr;      // scan scratch
-    uint32_t* tasks = nullptr;         // sorted task ids
-    uint32_t* len_hist = nullptr;      // histogram of task lengths
-    void* partial = nullptr;           // XYZZ per task
+    uint32_t* tasks = nullptr;         // t_start | t_len | task-sort alternates
+    uint32_t* counters = nullptr;      // [0] = number of tasks
     size_t cap_tasks = 0;
+    // results of the last digit stage (the sort ping-pongs between buffers)
+    uint32_t* s_vals = nullptr;        // point references sorted by bucket
+    uint32_t *s_tkeys = nullptr, *s_tvals = nullptr;  // tasks sorted by length: (kTaskLen - len, task id)
+    // batched-affine level tables (msm_affine.cu)
+    int ba_levels = 0;
+    size_t ba_stride = 0, ba_tstride = 0;
+    uint32_t* ba_start0 = nullptr;     // first sorted position of every bucket
+    uint32_t* ba_lvl = nullptr;        // [levels+1][nbuckets+1]: row 0 counts, rows 1.. offsets after each level
+    uint32_t* ba_tb = nullptr;         // [levels][2][tstride]: first / last bucket of every level-kernel thread
+    // -- point stage: per MSM ---------------------------------------------------------------------------------------------
+    void *ba_buf_a = nullptr, *ba_buf_b = nullptr;  // affine points after odd / even levels
+    void *ba_pre = nullptr, *ba_T = nullptr, *ba_Q = nullptr;  // Fq: prefix products per slot, thread totals, their inverses
+    void* partial = nullptr;           // XYZZ per task
     void* bucket_sum = nullptr;        // XYZZ per bucket
     void* chunk_sum = nullptr;         // XYZZ per chunk
     void* block_sum = nullptr;         // XYZZ per reduce block
     void* result = nullptr;            // XYZZ final (device)
-    uint32_t* counters = nullptr;      // misc device counters
     size_t point_bytes = 0;
 };
 
@@ -111,6 +124,9 @@ struct g16_ctx {
     void* d_small = nullptr;    // small device scratch for assembly
     g16_timings tm = {};
     int opt_serialize = 0, opt_kernel_events = 0, opt_window_bits = 0, opt_acc_variant = 0;
+    int opt_ba_levels = -1;  // batched-affine levels (-1 = default)
+    int opt_share_digits = 1;
+    bool share_al = false, share_b = false;  // l reuses a's digit stage / b_g2 reuses b_g1's
     cudaEvent_t ev_acc[10] = {};
     bool pre_pending = false;  // k_assemble_pre already in flight for (pre_r, pre_s)
     uint64_t pre_r[4] = {}, pre_s[4] = {};
@@ -181,8 +197,13 @@ int msm_set_bases(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, int group, const v
                   bool precomp, cudaStream_t st);
 void msm_free(MsmBases* mb, MsmScratch* sc);
 // runs Pippenger over the first n bases with device scalars (Montgomery Fr); leaves the XYZZ result in sc->result
+// `digits` (optional): scratch of another MSM that already ran over the SAME scalars on this stream, with the same
+// n / window / table geometry and skip pattern (msm_can_share): its sorted references and task lists are reused.
 int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st,
-            cudaEvent_t ev_acc0 = nullptr, cudaEvent_t ev_acc1 = nullptr);
+            cudaEvent_t ev_acc0 = nullptr, cudaEvent_t ev_acc1 = nullptr, const MsmScratch* digits = nullptr);
+// true when MSMs over `b` may reuse the digit stage of `a` (same geometry; every point `a` skips is infinity in `b` too
+// and `b` has at most `max_extra_inf` further points at infinity).  Synchronises the stream.
+int msm_can_share(g16_ctx* ctx, const MsmBases* a, const MsmBases* b, size_t max_extra_inf, bool* ok, cudaStream_t st);
 int fixed_base_dev(g16_ctx* ctx, int group, const Fr* scalars_dev, size_t n, void* out_pts_dev, cudaStream_t st);
 
 // assemble.cu -----------------------------------------------------------------------------------------------------------

@@ -5,291 +5,30 @@
 // the evaluation order.
 //
 // Pipeline (all on the device, stream-ordered, no host synchronisation):
+//   digit stage (depends on the scalars only; MSMs over the same scalars share it -- a/l and b_g1/b_g2 of a proof):
 //   1. k_digits        scalar (Montgomery) -> canonical -> W signed c-bit digits; emits (bucket key, point ref) pairs.
 //                      Zero digits and points at infinity get the EMPTY key.
-//   2. radix sort      hand-written LSD radix sort, 8 bits per pass, stable block-local ranking with warp match;
-//                      segments (= windows) never mix because histograms are laid out [segment][bin][tile].
+//   2. radix sort      msm_sort.cu: LSD radix sort of the pairs by bucket.
 //   3. k_bucket_bounds bucket start offsets from the sorted keys (no atomics).
-//   4. tasks           every bucket is cut into tasks of <= kTaskLen points; tasks are radix-sorted by length
-//                      (descending) so that the lanes of a warp run equally long loops whatever the scalar skew.
-//   5. k_accumulate    one thread per task: XYZZ mixed additions (8M + 2S each), next point prefetched.
-//   6. k_bucket_combine one warp per bucket folds that bucket's task partials (shuffle tree when there are several).
-//   7. k_chunk_reduce / k_tree_sum / k_finish
+//   4. level tables    msm_affine.cu: per-bucket counts/offsets after each batched-affine level.
+//   5. tasks           what is left of every bucket after the affine levels is cut into tasks of <= kTaskLen points;
+//                      tasks are radix-sorted by length (descending) so that the lanes of a warp run equally long loops
+//                      whatever the scalar skew.
+//   point stage (per MSM):
+//   6. batched-affine levels (msm_affine.cu): pairwise affine additions with shared inversions, ~6.5 Fq-mul each.
+//   7. k_accumulate    one thread per task: XYZZ mixed additions (8M + 2S each), next point prefetched.
+//   8. k_bucket_combine one warp per bucket folds that bucket's task partials (shuffle tree when there are several).
+//   9. k_chunk_reduce / k_tree_sum / k_finish
 //                      Sigma (b+1) * B_b per bucket set by chunked running sums + short double-and-add, tree sums,
 //                      and (without precomputation) the Horner combination of the windows.
 //
-// With `precomp` the bases hold 2^(c*w) * P_i for every window w, all windows share ONE bucket set and steps 7's
+// With `precomp` the bases hold 2^(c*w) * P_i for every window w, all windows share ONE bucket set and step 9's
 // Horner tail disappears: HBM capacity (180 GB) is traded for integer-pipe work.
-#include "internal.cuh"
+#include <stdlib.h>
+
+#include "msm_internal.cuh"
 
 namespace g16 {
-
-constexpr unsigned kTaskLen = 256;  // max points per accumulate task
-constexpr unsigned kChunk = 16;     // buckets per reduction chunk
-constexpr int kRsThreads = 256;
-constexpr int kRsItems = 16;
-constexpr int kRsTile = kRsThreads * kRsItems;  // 4096
-constexpr uint32_t kNegBit = 0x80000000u;
-
-template <class F>
-struct PointBytes {
-    static constexpr size_t affine = sizeof(Affine<F>);
-    static constexpr size_t xyzz = sizeof(XYZZ<F>);
-};
-
-// ---- vectorised loads/stores ------------------------------------------------------------------------------------------
-template <class T>
-__device__ __forceinline__ T ld_vec(const T* p) {
-    static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
-    T r;
-    const uint4* s = reinterpret_cast<const uint4*>(p);
-    uint4* d = reinterpret_cast<uint4*>(&r);
-#pragma unroll
-    for (unsigned i = 0; i < sizeof(T) / 16; i++) d[i] = s[i];
-    return r;
-}
-template <class T>
-__device__ __forceinline__ T ldg_vec(const T* p) {
-    T r;
-    const uint4* s = reinterpret_cast<const uint4*>(p);
-    uint4* d = reinterpret_cast<uint4*>(&r);
-#pragma unroll
-    for (unsigned i = 0; i < sizeof(T) / 16; i++) d[i] = __ldg(s + i);
-    return r;
-}
-template <class T>
-__device__ __forceinline__ void st_vec(T* p, const T& v) {
-    uint4* d = reinterpret_cast<uint4*>(p);
-    const uint4* s = reinterpret_cast<const uint4*>(&v);
-#pragma unroll
-    for (unsigned i = 0; i < sizeof(T) / 16; i++) d[i] = s[i];
-}
-
-// ---- generic exclusive scan (uint32), in place -------------------------------------------------------------------------
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
-
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* sh /*>= 33*/) {
-    // exclusive scan of one value per thread across a 256/1024-thread block; returns the prefix, *total = block sum
-    unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= (unsigned)o) x += y;
-    }
-    if (lane == 31) sh[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-        unsigned nw = (blockDim.x + 31) >> 5;
-        uint32_t s = lane < nw ? sh[lane] : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= (unsigned)o) s += y;
-        }
-        if (lane < nw) sh[lane] = s;  // inclusive warp totals
-        if (lane == nw - 1) sh[32] = s;
-    }
-    __syncthreads();
-    uint32_t base = wid ? sh[wid - 1] : 0;
-    *total = sh[32];
-    uint32_t r = base + x - v;
-    __syncthreads();
-    return r;
-}
-
-__global__ void k_scan_tile_sums(const uint32_t* __restrict__ data, size_t n, uint32_t* __restrict__ sums) {
-    __shared__ uint32_t sh[33];
-    size_t base = (size_t)blockIdx.x * kScanTile;
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        size_t i = base + (size_t)threadIdx.x * kScanItems + k;
-        if (i < n) s += data[i];
-    }
-    uint32_t tot;
-    block_exclusive_scan(s, &tot, sh);
-    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
-}
-__global__ void k_scan_single(uint32_t* __restrict__ data, size_t n, uint32_t* __restrict__ total_out) {
-    __shared__ uint32_t sh[33];
-    uint32_t carry = 0;
-    for (size_t base = 0; base < n; base += blockDim.x) {
-        size_t i = base + threadIdx.x;
-        uint32_t v = i < n ? data[i] : 0;
-        uint32_t tot;
-        uint32_t p = block_exclusive_scan(v, &tot, sh);
-        if (i < n) data[i] = carry + p;
-        carry += tot;
-    }
-    if (threadIdx.x == 0 && total_out) *total_out = carry;
-}
-__global__ void k_scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__ sums) {
-    __shared__ uint32_t sh[33];
-    size_t base = (size_t)blockIdx.x * kScanTile;
-    uint32_t v[kScanItems];
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        size_t i = base + (size_t)threadIdx.x * kScanItems + k;
-        v[k] = i < n ? data[i] : 0;
-        s += v[k];
-    }
-    uint32_t tot;
-    uint32_t p = block_exclusive_scan(s, &tot, sh) + sums[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        size_t i = base + (size_t)threadIdx.x * kScanItems + k;
-        if (i < n) data[i] = p;
-        p += v[k];
-    }
-}
-// data[0..n) -> exclusive prefix sums in place; tmp needs ceil(n / kScanTile) + 1 words; total (optional) device ptr
-static int exclusive_scan(g16_ctx* ctx, uint32_t* data, size_t n, uint32_t* tmp, uint32_t* total_dev, cudaStream_t st) {
-    if (n == 0) {
-        if (total_dev) G16_CUDA(ctx, cudaMemsetAsync(total_dev, 0, 4, st));
-        return G16_OK;
-    }
-    size_t tiles = (n + kScanTile - 1) / kScanTile;
-    if (tiles == 1) {
-        G16_LAUNCH(ctx, k_scan_single, 1, 1024, 0, st, data, n, total_dev);
-        return G16_OK;
-    }
-    G16_LAUNCH(ctx, k_scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, data, n, tmp);
-    G16_LAUNCH(ctx, k_scan_single, 1, 1024, 0, st, tmp, tiles, total_dev);
-    G16_LAUNCH(ctx, k_scan_apply, (unsigned)tiles, kScanThreads, 0, st, data, n, tmp);
-    return G16_OK;
-}
-
-// ---- LSD radix sort of (key, value) pairs, 8..11 bits per pass, segmented ------------------------------------------------
-// hist layout: [segment][bin][tile]  (flat exclusive scan => absolute output positions, segments stay separate
-// because every segment holds exactly seg_len items).  Wide digits keep the pass count at 2 for 20-bit bucket keys.
-constexpr unsigned kRsMaxBits = 11;
-
-template <unsigned BITS>
-__global__ void __launch_bounds__(kRsThreads)
-    k_rs_hist(const uint32_t* __restrict__ keys, size_t seg_len, unsigned tiles_per_seg, unsigned shift,
-              uint32_t* __restrict__ hist) {
-    constexpr unsigned NB = 1u << BITS;
-    __shared__ uint32_t sh[NB];
-    unsigned seg = blockIdx.x / tiles_per_seg, tile = blockIdx.x % tiles_per_seg;
-    for (unsigned b = threadIdx.x; b < NB; b += kRsThreads) sh[b] = 0;
-    __syncthreads();
-    size_t seg_base = (size_t)seg * seg_len;
-    size_t lo = (size_t)tile * kRsTile;
-#pragma unroll
-    for (int k = 0; k < kRsItems; k++) {
-        size_t i = lo + (size_t)k * kRsThreads + threadIdx.x;
-        if (i < seg_len) atomicAdd(&sh[(keys[seg_base + i] >> shift) & (NB - 1)], 1u);
-    }
-    __syncthreads();
-    for (unsigned b = threadIdx.x; b < NB; b += kRsThreads) hist[((size_t)seg * NB + b) * tiles_per_seg + tile] = sh[b];
-}
-
-template <unsigned BITS>
-__global__ void __launch_bounds__(kRsThreads)
-    k_rs_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t* __restrict__ okeys,
-                 uint32_t* __restrict__ ovals, size_t seg_len, unsigned tiles_per_seg, unsigned shift,
-                 const uint32_t* __restrict__ hist) {
-    constexpr unsigned NB = 1u << BITS;
-    constexpr unsigned NW = kRsThreads / 32;
-    extern __shared__ uint32_t wcnt[];  // [NW][NB]
-    unsigned seg = blockIdx.x / tiles_per_seg, tile = blockIdx.x % tiles_per_seg;
-    unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (unsigned i = threadIdx.x; i < NW * NB; i += kRsThreads) wcnt[i] = 0;
-    __syncthreads();
-    uint32_t* mine = wcnt + wid * NB;
-    size_t seg_base = (size_t)seg * seg_len;
-    // warp w owns items [w*512, (w+1)*512) of the tile, as 16 rows of 32: ranking order == index order (stable)
-    size_t lo = (size_t)tile * kRsTile + (size_t)wid * (32 * kRsItems);
-    uint32_t k[kRsItems], v[kRsItems];
-    uint32_t packed[kRsItems];  // rank within the row's digit group | group size << 8 | leader << 16 | valid << 17
-#pragma unroll
-    for (int r = 0; r < kRsItems; r++) {
-        size_t i = lo + (size_t)r * 32 + lane;
-        bool valid = i < seg_len;
-        k[r] = valid ? keys[seg_base + i] : 0xffffffffu;
-        v[r] = valid ? vals[seg_base + i] : 0u;
-        uint32_t d = valid ? ((k[r] >> shift) & (NB - 1)) : (NB + lane);
-        uint32_t mask = __match_any_sync(0xffffffffu, d);
-        uint32_t rank = __popc(mask & ((1u << lane) - 1u));
-        uint32_t cnt = __popc(mask);
-        bool leader = rank == 0;
-        packed[r] = rank | (cnt << 8) | ((leader && valid) ? 0x10000u : 0u) | (valid ? 0x20000u : 0u);
-        if (leader && valid) mine[d] += cnt;
-        __syncwarp();
-    }
-    __syncthreads();
-    for (unsigned bin = threadIdx.x; bin < NB; bin += kRsThreads) {
-        uint32_t run = hist[((size_t)seg * NB + bin) * tiles_per_seg + tile];
-#pragma unroll
-        for (unsigned w = 0; w < NW; w++) {
-            uint32_t t = wcnt[w * NB + bin];
-            wcnt[w * NB + bin] = run;
-            run += t;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < kRsItems; r++) {
-        bool valid = (packed[r] & 0x20000u) != 0;
-        uint32_t d = (k[r] >> shift) & (NB - 1);
-        uint32_t pos = 0;
-        if (valid) pos = mine[d] + (packed[r] & 0xffu);
-        __syncwarp();
-        if (packed[r] & 0x10000u) mine[d] += (packed[r] >> 8) & 0xffu;
-        __syncwarp();
-        if (valid) {
-            okeys[pos] = k[r];
-            ovals[pos] = v[r];
-        }
-    }
-}
-
-template <unsigned BITS>
-static int radix_pass(g16_ctx* ctx, const uint32_t* keys, const uint32_t* vals, uint32_t* okeys, uint32_t* ovals, size_t seg_len,
-                      unsigned nseg, unsigned tiles, unsigned shift, uint32_t* hist, uint32_t* scan_tmp, cudaStream_t st) {
-    constexpr unsigned NB = 1u << BITS;
-    const size_t smem = (size_t)(kRsThreads / 32) * NB * sizeof(uint32_t);
-    static bool attr_done = false;
-    if (!attr_done && smem > 48 * 1024) {
-        G16_CUDA(ctx, cudaFuncSetAttribute(k_rs_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    G16_LAUNCH(ctx, k_rs_hist<BITS>, nseg * tiles, kRsThreads, 0, st, keys, seg_len, tiles, shift, hist);
-    G16_TRY(exclusive_scan(ctx, hist, (size_t)nseg * NB * tiles, scan_tmp, nullptr, st));
-    G16_LAUNCH(ctx, k_rs_scatter<BITS>, nseg * tiles, kRsThreads, smem, st, keys, vals, okeys, ovals, seg_len, tiles, shift, hist);
-    return G16_OK;
-}
-
-static unsigned radix_digit_bits(unsigned bits) {
-    unsigned passes = (bits + kRsMaxBits - 1) / kRsMaxBits;
-    unsigned per = (bits + passes - 1) / passes;
-    return per < 8 ? 8 : per;
-}
-
-// sorts nseg segments of seg_len pairs by the low `bits` key bits; result ends in (*keys, *vals) (buffers may swap)
-static int radix_sort(g16_ctx* ctx, uint32_t** keys, uint32_t** vals, uint32_t** keys_alt, uint32_t** vals_alt,
-                      size_t seg_len, unsigned nseg, unsigned bits, uint32_t* hist, uint32_t* scan_tmp, cudaStream_t st) {
-    if (seg_len == 0 || nseg == 0) return G16_OK;
-    unsigned tiles = (unsigned)((seg_len + kRsTile - 1) / kRsTile);
-    unsigned per = radix_digit_bits(bits);
-    for (unsigned shift = 0; shift < bits; shift += per) {
-        int rc;
-        switch (per) {
-            case 8: rc = radix_pass<8>(ctx, *keys, *vals, *keys_alt, *vals_alt, seg_len, nseg, tiles, shift, hist, scan_tmp, st); break;
-            case 9: rc = radix_pass<9>(ctx, *keys, *vals, *keys_alt, *vals_alt, seg_len, nseg, tiles, shift, hist, scan_tmp, st); break;
-            case 10: rc = radix_pass<10>(ctx, *keys, *vals, *keys_alt, *vals_alt, seg_len, nseg, tiles, shift, hist, scan_tmp, st); break;
-            default: rc = radix_pass<11>(ctx, *keys, *vals, *keys_alt, *vals_alt, seg_len, nseg, tiles, shift, hist, scan_tmp, st); break;
-        }
-        G16_TRY(rc);
-        std::swap(*keys, *keys_alt);
-        std::swap(*vals, *vals_alt);
-    }
-    return G16_OK;
-}
 
 // ---- 1. signed-digit decomposition ---------------------------------------------------------------------------------------
 // pair position = w * n + i.  value = base index | sign; base index = i (plain) or w * n_bases + i (precomputed table).
@@ -339,45 +78,48 @@ __global__ void k_bucket_bounds(const uint32_t* __restrict__ keys, size_t seg_le
         for (int64_t b = (int64_t)k + 1; b <= (int64_t)nb; b++) st[b] = (uint32_t)(g + 1);
 }
 
-// ---- 4. tasks ----------------------------------------------------------------------------------------------------------------
-__global__ void k_task_counts(const uint32_t* __restrict__ start, unsigned nseg, uint32_t nb, uint32_t* __restrict__ ntasks) {
+// ---- 5. tasks ----------------------------------------------------------------------------------------------------------------
+// Bucket g holds cnt points at positions [start[g], start[g] + cnt) of the point list the accumulate kernel reads
+// (cnt == nullptr: start is an offset table with nbuckets + 1 entries).
+__device__ __forceinline__ uint32_t bucket_count(const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt, size_t g) {
+    return cnt ? cnt[g] : start[g + 1] - start[g];
+}
+// buckets with at most `direct_max` points get no task: k_bucket_tail sums them with one thread each
+__global__ void k_task_counts(const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt, size_t nbuckets,
+                              uint32_t direct_max, uint32_t task_len, uint32_t* __restrict__ ntasks) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)nseg * nb;
-    if (g >= total) return;
-    unsigned seg = (unsigned)(g / nb);
-    uint32_t b = (uint32_t)(g - (size_t)seg * nb);
-    const uint32_t* st = start + (size_t)seg * (nb + 1);
-    uint32_t cnt = st[b + 1] - st[b];
-    ntasks[g] = (cnt + kTaskLen - 1) / kTaskLen;
+    if (g >= nbuckets) return;
+    uint32_t c = bucket_count(start, cnt, g);
+    ntasks[g] = c > direct_max ? (c + task_len - 1) / task_len : 0;
 }
 __global__ void k_fill_u32(uint32_t* __restrict__ p, uint32_t v, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) p[i] = v;
 }
-// task t of bucket g covers sorted positions [start + j*L, ...); sort key = kTaskLen - len (longest first)
-__global__ void k_make_tasks(const uint32_t* __restrict__ start, const uint32_t* __restrict__ task_off, unsigned nseg,
-                             uint32_t nb, uint32_t* __restrict__ tkeys, uint32_t* __restrict__ tvals,
-                             uint32_t* __restrict__ t_start, uint32_t* __restrict__ t_len) {
+// task t of bucket g covers positions [start + j*task_len, ...); sort key = task_len - len (longest first)
+__global__ void k_make_tasks(const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt_tab,
+                             const uint32_t* __restrict__ task_off, size_t nbuckets, uint32_t direct_max, uint32_t task_len,
+                             uint32_t* __restrict__ tkeys, uint32_t* __restrict__ tvals, uint32_t* __restrict__ t_start,
+                             uint32_t* __restrict__ t_len) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)nseg * nb;
-    if (g >= total) return;
-    unsigned seg = (unsigned)(g / nb);
-    uint32_t b = (uint32_t)(g - (size_t)seg * nb);
-    const uint32_t* st = start + (size_t)seg * (nb + 1);
-    uint32_t s0 = st[b], cnt = st[b + 1] - s0;
+    if (g >= nbuckets) return;
+    uint32_t s0 = start[g], cnt = bucket_count(start, cnt_tab, g);
+    if (cnt <= direct_max) return;
     uint32_t t = task_off[g];
-    for (uint32_t o = 0; o < cnt; o += kTaskLen, t++) {
-        uint32_t len = cnt - o < kTaskLen ? cnt - o : kTaskLen;
+    for (uint32_t o = 0; o < cnt; o += task_len, t++) {
+        uint32_t len = cnt - o < task_len ? cnt - o : task_len;
         t_start[t] = s0 + o;
         t_len[t] = len;
-        tkeys[t] = kTaskLen - len;
+        tkeys[t] = task_len - len;
         tvals[t] = t;
     }
 }
 
-// ---- 5. bucket accumulation --------------------------------------------------------------------------------------------------
-template <class F, int MINB>
+// ---- 7. bucket accumulation (XYZZ) ------------------------------------------------------------------------------------------
+// DIRECT = false: points are gathered from the base table through the sorted references (sign in the top bit);
+// DIRECT = true: the task ranges index `bases` itself (the survivors of the batched-affine levels, sign already applied).
+template <class F, int MINB, bool DIRECT>
 __global__ void __launch_bounds__(128, MINB)
     k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ vals,
                  const uint32_t* __restrict__ order_keys, const uint32_t* __restrict__ order,
@@ -389,23 +131,39 @@ __global__ void __launch_bounds__(128, MINB)
         uint32_t t = order[p];
         uint32_t s0 = t_start[t], len = t_len[t];
         XYZZ<F> acc = XYZZ<F>::inf();
-        uint32_t ref = vals[s0];
+        uint32_t ref = DIRECT ? s0 : vals[s0];
         Affine<F> nxt = ldg_vec(bases + (ref & ~kNegBit));
         for (uint32_t k = 0; k < len; k++) {
             Affine<F> cur = nxt;
             uint32_t cref = ref;
             if (k + 1 < len) {
-                ref = vals[s0 + k + 1];
+                ref = DIRECT ? s0 + k + 1 : vals[s0 + k + 1];
                 nxt = ldg_vec(bases + (ref & ~kNegBit));
             }
-            if (cref & kNegBit) cur.y = cur.y.neg();
+            if (!DIRECT && (cref & kNegBit)) cur.y = cur.y.neg();
             acc.madd(cur);
         }
         st_vec(partial + t, acc);
     }
 }
 
-// ---- 6. per-bucket combine (one warp per bucket) ----------------------------------------------------------------------------
+// Survivors of the batched-affine levels: almost every bucket holds one or two points, so one thread sums a whole
+// bucket straight into bucket_sum (consecutive buckets are consecutive in memory: no task indirection, no combine).
+// Buckets above kTailDirect points (skewed scalars) are left to the task path.
+template <class F>
+__global__ void __launch_bounds__(128)
+    k_bucket_tail(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ off, size_t nbuckets,
+                  XYZZ<F>* __restrict__ bucket_sum) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nbuckets) return;
+    uint32_t s0 = off[g], cnt = off[g + 1] - s0;
+    if (cnt > kTailDirect) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = 0; k < cnt; k++) acc.madd(ld_vec(pts + s0 + k));
+    st_vec(bucket_sum + g, acc);
+}
+
+// ---- 8. per-bucket combine (one warp per bucket) ----------------------------------------------------------------------------
 template <class F>
 __device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& a, unsigned delta) {
     XYZZ<F> r;
@@ -419,7 +177,8 @@ __device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& a, unsigned del
 template <class F>
 __global__ void __launch_bounds__(128)
     k_bucket_combine(const XYZZ<F>* __restrict__ partial, const uint32_t* __restrict__ task_off,
-                     const uint32_t* __restrict__ total_tasks, size_t nbuckets, XYZZ<F>* __restrict__ bucket_sum) {
+                     const uint32_t* __restrict__ total_tasks, size_t nbuckets, int keep_untasked,
+                     XYZZ<F>* __restrict__ bucket_sum) {
     size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned lane = threadIdx.x & 31;
     size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -427,6 +186,7 @@ __global__ void __launch_bounds__(128)
         uint32_t t0 = task_off[b];
         uint32_t t1 = (b + 1 < nbuckets) ? task_off[b + 1] : *total_tasks;
         uint32_t cnt = t1 - t0;
+        if (cnt == 0 && keep_untasked) continue;  // k_bucket_tail already wrote this bucket
         if (cnt <= 1) {
             if (lane == 0) {
                 XYZZ<F> v = cnt ? ld_vec(partial + t0) : XYZZ<F>::inf();
@@ -445,7 +205,7 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-// ---- 7. bucket-set reduction:  S = Sigma_{b} (b + 1) * B_b ------------------------------------------------------------------
+// ---- 9. bucket-set reduction:  S = Sigma_{b} (b + 1) * B_b ------------------------------------------------------------------
 // chunk k of a set holds buckets [k*kChunk, (k+1)*kChunk): running sums give acc = Sigma (j+1) B_{lo+j}, run = Sigma B;
 // contribution = acc + lo * run with lo = k*kChunk applied by a short double-and-add.
 template <class F>
@@ -557,7 +317,15 @@ int msm_pick_window(size_t n, int group, bool precomp) {
     return c;
 }
 
-static size_t task_capacity(size_t items, size_t nbuckets) { return items / kTaskLen + nbuckets + 1; }
+// XYZZ-only path: every non-empty bucket is cut into tasks of <= kTaskLen points.  After batched-affine levels only the
+// buckets that still hold more than kTailDirect points (skewed scalars; the short top window) get tasks, of kTaskLenDirect
+// points so that their few threads do not become a latency tail.
+constexpr uint32_t kTaskLenDirect = 16;
+static size_t task_capacity(size_t items, size_t nbuckets, int levels) {
+    if (levels == 0) return items / kTaskLen + nbuckets + 1;
+    size_t pts = ba_level_cap(items, nbuckets, levels);
+    return pts / kTaskLenDirect + pts / kTailDirect + 2;
+}
 
 template <class F>
 static int msm_alloc_scratch(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc) {
@@ -567,13 +335,11 @@ static int msm_alloc_scratch(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc) {
     const unsigned nseg = mb->precomp ? 1 : W;
     size_t items = n * W;
     size_t nbuckets = (size_t)nseg * nb;
-    size_t tcap = task_capacity(items, nbuckets);
+    size_t tcap = task_capacity(items, nbuckets, mb->ba_levels);
     size_t sort_n = items > tcap ? items : tcap;
     size_t seg_len = mb->precomp ? items : n;
-    size_t tiles = (seg_len + kRsTile - 1) / kRsTile;
-    size_t hist_n = (size_t)nseg * (1u << kRsMaxBits) * tiles;
-    size_t ttiles = (tcap + kRsTile - 1) / kRsTile;
-    if ((size_t)(1u << kRsMaxBits) * ttiles > hist_n) hist_n = (size_t)(1u << kRsMaxBits) * ttiles;
+    size_t hist_n = radix_hist_words(seg_len, nseg);
+    if (radix_hist_words(tcap, 1) > hist_n) hist_n = radix_hist_words(tcap, 1);
     sc->cap_items = items;
     sc->cap_buckets = nbuckets;
     sc->cap_tasks = tcap;
@@ -585,10 +351,12 @@ static int msm_alloc_scratch(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc) {
     G16_TRY(dev_alloc(ctx, &sc->hist, hist_n));
     G16_TRY(dev_alloc(ctx, &sc->bucket_start, (size_t)nseg * (nb + 1)));
     G16_TRY(dev_alloc(ctx, &sc->task_off, nbuckets + 1));
-    size_t scan_tmp = (hist_n > nbuckets ? hist_n : nbuckets) / kScanTile + 2;
+    size_t scan_tmp = scan_tmp_words(hist_n);
+    if ((size_t)(mb->ba_levels + 1) * scan_tmp_words(nbuckets + 1) > scan_tmp) scan_tmp = (size_t)(mb->ba_levels + 1) * scan_tmp_words(nbuckets + 1);
     G16_TRY(dev_alloc(ctx, &sc->task_tmp, scan_tmp));
     G16_TRY(dev_alloc(ctx, &sc->tasks, 4 * tcap));  // t_start | t_len | task-sort alternates (keys, order)
     G16_TRY(dev_alloc(ctx, &sc->counters, 16));
+    G16_TRY(ba_alloc(ctx, mb->group, sc, items, nbuckets, mb->ba_levels));
     size_t chunks = (size_t)nseg * ((nb + kChunk - 1) / kChunk);
     XYZZ<F>* p;
     G16_TRY(dev_alloc(ctx, &p, tcap));
@@ -619,6 +387,7 @@ void msm_free(MsmBases* mb, MsmScratch* sc) {
     dev_free(sc->task_tmp);
     dev_free(sc->tasks);
     dev_free(sc->counters);
+    ba_free(sc);
     dev_free(sc->partial);
     dev_free(sc->bucket_sum);
     dev_free(sc->chunk_sum);
@@ -637,6 +406,8 @@ static int msm_set_bases_t(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const voi
     if (mb->c < 2 || mb->c > 24) return set_err(ctx, G16_ERR_BAD_ARG, "window bits %d out of range", mb->c);
     mb->windows = (255 + mb->c - 1) / mb->c;
     mb->precomp = precomp;
+    mb->ba_levels = ctx->opt_ba_levels < 0 ? kBaDefaultLevels : ctx->opt_ba_levels;
+    if (mb->ba_levels > kBaMaxLevels) mb->ba_levels = kBaMaxLevels;
     if ((size_t)mb->windows * (n ? n : 1) >= ((size_t)1 << 31))
         return set_err(ctx, G16_ERR_BAD_ARG, "MSM of %zu points x %d windows exceeds 2^31 pair references", n, mb->windows);
     if (n == 0) return G16_OK;
@@ -660,22 +431,46 @@ int msm_set_bases(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, int group, const v
     return set_err(ctx, G16_ERR_BAD_ARG, "group must be 1 or 2");
 }
 
-template <class F>
-static int msm_run_t(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars, size_t n, cudaStream_t st, cudaEvent_t ev0,
-                     cudaEvent_t ev1) {
-    XYZZ<F>* result = (XYZZ<F>*)sc->result;
-    if (n > mb->n) return set_err(ctx, G16_ERR_BAD_ARG, "msm: %zu scalars for %zu bases", n, mb->n);
-    if (n == 0 || mb->n == 0) {
-        if (result) G16_CUDA(ctx, cudaMemsetAsync(result, 0, sizeof(XYZZ<F>), st));
-        return G16_OK;
+// counts[0] = points a skips that b does not; counts[1] = points b skips that a does not
+__global__ void k_skip_diff(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, unsigned long long* counts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long only_a = 0, only_b = 0;
+    for (; i < n; i += stride) {
+        only_a += a[i] && !b[i];
+        only_b += b[i] && !a[i];
     }
+    if (only_a) atomicAdd(counts, only_a);
+    if (only_b) atomicAdd(counts + 1, only_b);
+}
+
+int msm_can_share(g16_ctx* ctx, const MsmBases* a, const MsmBases* b, size_t max_extra_inf, bool* ok, cudaStream_t st) {
+    *ok = false;
+    if (a->n == 0 || a->n != b->n || a->c != b->c || a->windows != b->windows || a->precomp != b->precomp ||
+        a->ba_levels != b->ba_levels)
+        return G16_OK;
+    unsigned long long* d = (unsigned long long*)((char*)ctx->d_small + 3072);  // past the assembly scratch
+    G16_CUDA(ctx, cudaMemsetAsync(d, 0, 16, st));
+    G16_LAUNCH(ctx, k_skip_diff, kNumSMs * 2, 256, 0, st, a->skip, b->skip, a->n, d);
+    unsigned long long h[2];
+    G16_CUDA(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, st));
+    G16_CUDA(ctx, cudaStreamSynchronize(st));
+    // a point only `a` skips would be lost for `b`; a point only `b` skips is an infinity entry of b's table that the
+    // addition kernels pass over (costs an idle lane, so only a few are tolerated)
+    *ok = h[0] == 0 && h[1] <= max_extra_inf;
+    return G16_OK;
+}
+
+// ---- digit stage: steps 1-5 ------------------------------------------------------------------------------------------------
+static int msm_digit_stage(g16_ctx* ctx, const MsmBases* mb, MsmScratch* sc, const Fr* scalars, size_t n, cudaStream_t st) {
     const unsigned W = mb->windows, c = mb->c;
     const uint32_t nb = 1u << (c - 1);
     const unsigned nseg = mb->precomp ? 1 : W;
     const size_t items = n * W;
     const size_t seg_len = mb->precomp ? items : n;
     const size_t nbuckets = (size_t)nseg * nb;
-    const size_t tcap = task_capacity(items, nbuckets);
+    const int L = mb->ba_levels;
+    const size_t tcap = task_capacity(items, nbuckets, L);
     unsigned key_bits = c;  // keys in [0, nb] need c bits (nb = 2^(c-1) is the EMPTY key)
 
     // 1. digits
@@ -684,54 +479,82 @@ static int msm_run_t(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scala
     // 2. sort pairs by bucket
     uint32_t *keys = sc->keys_a, *vals = sc->vals_a, *keys2 = sc->keys_b, *vals2 = sc->vals_b;
     G16_TRY(radix_sort(ctx, &keys, &vals, &keys2, &vals2, seg_len, nseg, key_bits, sc->hist, sc->task_tmp, st));
+    sc->s_vals = vals;
     // 3. bucket boundaries
     G16_LAUNCH(ctx, k_bucket_bounds, (unsigned)((items + 255) / 256), 256, 0, st, keys, seg_len, nseg, nb, sc->bucket_start);
-    // 4. tasks: counts -> offsets -> descriptors -> sort by length (descending)
-    G16_LAUNCH(ctx, k_task_counts, (unsigned)((nbuckets + 255) / 256), 256, 0, st, sc->bucket_start, nseg, nb, sc->task_off);
+    // 4. per-level bucket counts / offsets
+    G16_TRY(ba_build_levels(ctx, sc, nseg, nb, L, st));
+    // 5. tasks over what the affine levels leave: counts -> offsets -> descriptors -> sort by length (descending)
+    const uint32_t* tstart = L ? sc->ba_lvl + (size_t)L * sc->ba_stride : sc->ba_start0;
+    const uint32_t* tcnt = L ? nullptr : sc->ba_lvl;
+    const uint32_t direct_max = L ? kTailDirect : 0;
+    const uint32_t task_len = L ? kTaskLenDirect : kTaskLen;
+    G16_LAUNCH(ctx, k_task_counts, (unsigned)((nbuckets + 255) / 256), 256, 0, st, tstart, tcnt, nbuckets, direct_max, task_len, sc->task_off);
     G16_TRY(exclusive_scan(ctx, sc->task_off, nbuckets, sc->task_tmp, sc->counters, st));
     uint32_t *tkeys = keys2, *tvals = vals2;  // the alternate sort buffers are free now
-    uint32_t *tkeys2 = sc->keys_a == keys ? nullptr : nullptr;
-    (void)tkeys2;
     G16_LAUNCH(ctx, k_fill_u32, kNumSMs * 4, 256, 0, st, tkeys, (uint32_t)kTaskLen, tcap);
     uint32_t* t_start = sc->tasks;
-    uint32_t* t_len = sc->tasks + tcap;
-    G16_LAUNCH(ctx, k_make_tasks, (unsigned)((nbuckets + 255) / 256), 256, 0, st, sc->bucket_start, sc->task_off, nseg, nb,
-               tkeys, tvals, t_start, t_len);
-    uint32_t* tk_alt = sc->tasks + 2 * tcap;  // dedicated: with one 9-bit pass the sorted order ENDS in the alternates,
-    uint32_t* tv_alt = sc->tasks + 3 * tcap;  // which k_accumulate reads while it writes sc->partial
-    {
-        uint32_t *a = tkeys, *b = tvals, *a2 = tk_alt, *b2 = tv_alt;
-        G16_TRY(radix_sort(ctx, &a, &b, &a2, &b2, tcap, 1, 9, sc->hist, sc->task_tmp, st));
-        tkeys = a;
-        tvals = b;
-    }
-    // 5. accumulate
+    uint32_t* t_len = sc->tasks + sc->cap_tasks;
+    G16_LAUNCH(ctx, k_make_tasks, (unsigned)((nbuckets + 255) / 256), 256, 0, st, tstart, tcnt, sc->task_off, nbuckets, direct_max,
+               task_len, tkeys, tvals, t_start, t_len);
+    uint32_t* tk_alt = sc->tasks + 2 * sc->cap_tasks;  // dedicated: with one 9-bit pass the sorted order ENDS in the alternates,
+    uint32_t* tv_alt = sc->tasks + 3 * sc->cap_tasks;  // which k_accumulate reads while it writes sc->partial
+    G16_TRY(radix_sort(ctx, &tkeys, &tvals, &tk_alt, &tv_alt, tcap, 1, 9, sc->hist, sc->task_tmp, st));
+    sc->s_tkeys = tkeys;
+    sc->s_tvals = tvals;
+    return G16_OK;
+}
+
+// ---- point stage: steps 6-9 --------------------------------------------------------------------------------------------------
+template <class F>
+static int msm_point_stage(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const MsmScratch* dg, size_t n, cudaStream_t st,
+                           cudaEvent_t ev0, cudaEvent_t ev1) {
+    XYZZ<F>* result = (XYZZ<F>*)sc->result;
+    const unsigned W = mb->windows, c = mb->c;
+    const uint32_t nb = 1u << (c - 1);
+    const unsigned nseg = mb->precomp ? 1 : W;
+    const size_t items = n * W;
+    const size_t nbuckets = (size_t)nseg * nb;
+    const int L = mb->ba_levels;
+    const size_t tcap = task_capacity(items, nbuckets, L);
+    const uint32_t* t_start = dg->tasks;
+    const uint32_t* t_len = dg->tasks + dg->cap_tasks;
+    if (ev0) G16_CUDA(ctx, cudaEventRecord(ev0, st));
+    // 6. batched-affine levels
+    const void* pts = mb->pts;
+    if (L) G16_TRY(ba_run_levels(ctx, mb, sc, dg, items, nbuckets, L, &pts, st));
+    // 7. accumulate the survivors
     {
         size_t want = (tcap + 127) / 128;
         unsigned grid = (unsigned)(want < (size_t)kNumSMs * 8 ? want : (size_t)kNumSMs * 8);
-        if (ev0) G16_CUDA(ctx, cudaEventRecord(ev0, st));
-        const int variant = ctx->opt_acc_variant;
-#define G16_ACC(MINB)                                                                                                        \
-    G16_LAUNCH(ctx, (k_accumulate<F, MINB>), grid, 128, 0, st, (const Affine<F>*)mb->pts, vals, tkeys, tvals, t_start, t_len, \
-               (XYZZ<F>*)sc->partial, tcap)
-        if constexpr (sizeof(F) == sizeof(Fq)) {
-            if (variant == 4) G16_ACC(4);
-            else G16_ACC(3);  // 148 registers, no spills; occupancy beyond 3 blocks/SM buys nothing (measured)
-        } else {
-            if (variant == 2) G16_ACC(2);
-            else G16_ACC(3);  // 168 registers with out-of-line Fq2 products
-        }
-#undef G16_ACC
-        if (ev1) G16_CUDA(ctx, cudaEventRecord(ev1, st));
+        if (L) {
+            G16_LAUNCH(ctx, k_bucket_tail<F>, (unsigned)((nbuckets + 127) / 128), 128, 0, st, (const Affine<F>*)pts,
+                       dg->ba_lvl + (size_t)L * dg->ba_stride, nbuckets, (XYZZ<F>*)sc->bucket_sum);
+            G16_LAUNCH(ctx, (k_accumulate<F, 3, true>), grid, 128, 0, st, (const Affine<F>*)pts, (const uint32_t*)nullptr, dg->s_tkeys,
+                       dg->s_tvals, t_start, t_len, (XYZZ<F>*)sc->partial, tcap);
+        } else
+            G16_LAUNCH(ctx, (k_accumulate<F, 3, false>), grid, 128, 0, st, (const Affine<F>*)pts, dg->s_vals, dg->s_tkeys, dg->s_tvals,
+                       t_start, t_len, (XYZZ<F>*)sc->partial, tcap);
     }
-    // 6. combine task partials per bucket
+    if (ev1) G16_CUDA(ctx, cudaEventRecord(ev1, st));
+    if (getenv("G16_DEBUG_MSM")) {  // diagnostics only: synchronises
+        uint32_t ntasks = 0, totals[kBaMaxLevels + 1] = {};
+        cudaStreamSynchronize(st);
+        cudaMemcpy(&ntasks, dg->counters, 4, cudaMemcpyDeviceToHost);
+        for (int k = 1; k <= L; k++) cudaMemcpy(&totals[k], dg->ba_lvl + (size_t)k * dg->ba_stride + nbuckets, 4, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[g16 msm] group %d n %zu items %zu buckets %zu levels %d tcap %zu tasks %u level totals:", mb->group, n, items,
+                nbuckets, L, tcap, ntasks);
+        for (int k = 1; k <= L; k++) fprintf(stderr, " %u", totals[k]);
+        fprintf(stderr, "\n");
+    }
+    // 8. combine task partials per bucket
     {
         size_t want = (nbuckets * 32 + 127) / 128;
         unsigned grid = (unsigned)(want < (size_t)kNumSMs * 32 ? want : (size_t)kNumSMs * 32);
-        G16_LAUNCH(ctx, k_bucket_combine<F>, grid, 128, 0, st, (const XYZZ<F>*)sc->partial, sc->task_off, sc->counters,
-                   nbuckets, (XYZZ<F>*)sc->bucket_sum);
+        G16_LAUNCH(ctx, k_bucket_combine<F>, grid, 128, 0, st, (const XYZZ<F>*)sc->partial, dg->task_off, dg->counters,
+                   nbuckets, (int)(L != 0), (XYZZ<F>*)sc->bucket_sum);
     }
-    // 7. reduce every bucket set, then combine the windows
+    // 9. reduce every bucket set, then combine the windows
     {
         uint32_t chunks_per_seg = (nb + kChunk - 1) / kChunk;
         size_t chunks = (size_t)nseg * chunks_per_seg;
@@ -750,10 +573,21 @@ static int msm_run_t(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scala
 }
 
 int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st, cudaEvent_t ev0,
-            cudaEvent_t ev1) {
-    if (mb->group == 1) return msm_run_t<Fq>(ctx, mb, sc, scalars_dev, n, st, ev0, ev1);
-    if (mb->group == 2) return msm_run_t<Fq2>(ctx, mb, sc, scalars_dev, n, st, ev0, ev1);
-    return set_err(ctx, G16_ERR_BAD_ARG, "msm: bases not set");
+            cudaEvent_t ev1, const MsmScratch* digits) {
+    if (mb->group != 1 && mb->group != 2) return set_err(ctx, G16_ERR_BAD_ARG, "msm: bases not set");
+    if (n > mb->n) return set_err(ctx, G16_ERR_BAD_ARG, "msm: %zu scalars for %zu bases", n, mb->n);
+    if (n == 0 || mb->n == 0) {
+        if (sc->result) G16_CUDA(ctx, cudaMemsetAsync(sc->result, 0, mb->group == 1 ? sizeof(G1XYZZ) : sizeof(G2XYZZ), st));
+        return G16_OK;
+    }
+    if (!digits) {
+        G16_TRY(msm_digit_stage(ctx, mb, sc, scalars_dev, n, st));
+        digits = sc;
+    } else if (digits->cap_items != sc->cap_items || digits->cap_buckets != sc->cap_buckets || digits->ba_levels != sc->ba_levels) {
+        return set_err(ctx, G16_ERR_BAD_ARG, "msm: shared digit stage has a different geometry");
+    }
+    if (mb->group == 1) return msm_point_stage<Fq>(ctx, mb, sc, digits, n, st, ev0, ev1);
+    return msm_point_stage<Fq2>(ctx, mb, sc, digits, n, st, ev0, ev1);
 }
 
 // canonical generators in Montgomery form are produced on the host from their canonical coordinates

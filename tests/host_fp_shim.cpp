@@ -17,6 +17,7 @@ template <class F> static void bin(int op, const uint32_t* a, const uint32_t* b,
         case 6: z = x.from_mont(); break;
         case 7: z = x.sqr(); break;
         case 8: z = F::mul_karatsuba(x, y); break;
+        case 9: z = x.inverse_bgcd(); break;
         default: z = F::zero();
     }
     memcpy(r, z.v, 32);

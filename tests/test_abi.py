@@ -88,6 +88,10 @@ def test_device_montgomery_code_on_host_matches_oracle(host_fp, name, p):
         assert dec(_call(fn, 6, le(a), le(0))) == a * rinv % p
     for a in vals[1:30]:
         assert dec(_call(fn, 4, le((a << 256) % p), le(0))) == (pow(a, -1, p) << 256) % p
+    # binary-GCD inverse (the one the batched-affine MSM uses): same answers, and 0 -> 0
+    for a in vals[1:400]:
+        assert dec(_call(fn, 9, le((a << 256) % p), le(0))) == (pow(a, -1, p) << 256) % p
+    assert dec(_call(fn, 9, le(0), le(0))) == 0
 
 
 def test_device_fq2_code_on_host_matches_oracle(host_fp):

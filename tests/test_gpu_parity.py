@@ -241,3 +241,53 @@ def test_msm_window_sizes(gpu_ctx, c):
     finally:
         gpu_ctx.set_option("window_bits", 0)
     assert g.g1_from_mont(out, inf) == o.G1.to_affine(o.G1.msm(pts, sc))
+
+
+@pytest.mark.parametrize("levels", [0, 1, 2, 3, 8])
+def test_msm_batched_affine_levels(gpu_ctx, levels):
+    """Every split between batched-affine levels and the XYZZ tail gives the same group element (G1 and G2), including
+    infinity points, repeated points (tangent case), P + (-P) pairs and one heavily loaded bucket (equal scalars)."""
+    n = 260
+    pts, sc = _points(o.G1, n, 51), _scalars(n, 52)
+    pts[10] = pts[11] = pts[12] = pts[13]          # same point, and ...
+    sc[10] = sc[11] = sc[12] = sc[13] = 0x1234567  # ... same digits: P + P inside a bucket at level 0 and 2P + 2P at level 1
+    pts[21] = o.G1.neg(pts[20])
+    sc[20] = sc[21] = 0xABCDEF                     # P + (-P) inside a bucket
+    for i in range(100, 230):
+        sc[i] = 3                                  # one bucket with 130 points: survivors go through the task path or the
+                                                   # one-thread tail depending on the number of levels
+    gpu_ctx.set_option("ba_levels", levels)
+    try:
+        out, inf = gpu_ctx.msm(1, g.g1_points_to_mont(pts), g.fr_to_mont(sc))
+        assert g.g1_from_mont(out, inf) == o.G1.to_affine(o.G1.msm(pts, sc))
+        n2 = 70
+        p2, s2 = _points(o.G2, n2, 53), _scalars(n2, 54)
+        p2[4] = p2[5] = p2[6]
+        s2[4] = s2[5] = s2[6] = 0x7654321
+        p2[9] = o.G2.neg(p2[8])
+        s2[8] = s2[9] = 0x13579B
+        for i in range(30, 50):
+            s2[i] = 5
+        out, inf = gpu_ctx.msm(2, g.g2_points_to_mont(p2), g.fr_to_mont(s2))
+        assert g.g2_from_mont(out, inf) == o.G2.to_affine(o.G2.msm(p2, s2))
+    finally:
+        gpu_ctx.set_option("ba_levels", -1)
+
+
+@pytest.mark.parametrize("share,levels", [(0, 0), (0, 5), (1, 0), (1, 5)])
+def test_golden_prove_digit_sharing(share, levels):
+    """l reusing a's digit stage and b_g2 reusing b_g1's (and the batched-affine levels) do not change a proof byte."""
+    for name in ("rand300", "dummy924_nozk"):
+        meta, r1cs_bytes, pk_bytes = load_golden(name)
+        mats = load_matrices(r1cs_bytes)
+        pk = g.ProvingKey.deserialize_uncompressed_unchecked(pk_bytes)
+        prover = g.Groth16(0, precompute=True)
+        prover.ctx.set_option("share_digits", share)
+        prover.ctx.set_option("ba_levels", levels)
+        try:
+            z = [int(v, 16) for v in meta["z"]]
+            proof = prover.create_proof_with_reduction_and_matrices(pk, int(meta["r"], 16), int(meta["s"], 16), mats,
+                                                                    mats.num_instance_variables, mats.num_constraints, z)
+            assert proof.serialize_uncompressed().hex() == meta["proof_uncompressed"]
+        finally:
+            prover.close()

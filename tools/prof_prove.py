@@ -21,6 +21,8 @@ ap.add_argument("--precompute", type=int, default=0)
 ap.add_argument("--window-bits", type=int, default=0)
 ap.add_argument("--serialize", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--ba-levels", type=int, default=-1)
+ap.add_argument("--share-digits", type=int, default=1)
 args = ap.parse_args()
 tstream = torch.cuda.Stream()
 torch.cuda.set_stream(tstream)
@@ -29,6 +31,8 @@ if args.window_bits:
     ctx.set_option("window_bits", args.window_bits)
 inst, pk, qap, td = build_problem(ctx, args.workload, args.witness)
 ctx.load_r1cs(inst.nc, inst.ni, inst.m, inst.matrices.row_ptr, inst.matrices.col, inst.matrices.val, inst.matrices.encoding)
+ctx.set_option("ba_levels", args.ba_levels)
+ctx.set_option("share_digits", args.share_digits)
 ctx.load_pk(pk.arrays, pk.encoding, 0, 1, bool(args.precompute))
 r_m, s_m = g.fr_to_mont([12345])[0], g.fr_to_mont([67890])[0]
 ctx.upload_witness(inst.z_mont)
