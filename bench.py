@@ -8,7 +8,7 @@ One step = one full Groth16 proof (witness map + 5 MSMs + assembly) of the workl
   value : proofs/s with the witness already resident in HBM (g16_prove_resident), device-timed
   e2e   : proofs/s through the public call g16_prove with a pinned HOST witness (H2D inside) and the proof read back
 N > 1   : the five MSMs are sharded by point range over N ranks (one process per GPU, torchrun); every rank runs the
-          witness map; partial sums are gathered with one NCCL all_gather of 768 B; rank 0 assembles.  Fixed total
+          witness map; partial sums are gathered with one NCCL all_gather of 896 B; rank 0 assembles.  Fixed total
           work => "scaling": "strong".
 Inputs exceed L2 (pk + scratch >> 126 MB), so no explicit L2 flush is needed between steps (config.l2: "inputs>L2").
 """
@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--ba-levels", type=int, default=-1, help="batched-affine levels before the XYZZ tail (-1 = library default)")
     ap.add_argument("--share-digits", type=int, default=1)
+    ap.add_argument("--main-priority", type=int, default=0, help="priority of the torch stream the library uses as its main stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     args = ap.parse_args()
@@ -187,7 +188,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # a real (non-default) torch stream is the library's main stream: torch events and NCCL calls are ordered with it
-    tstream = torch.cuda.Stream()
+    tstream = torch.cuda.Stream(priority=args.main_priority)
     torch.cuda.set_stream(tstream)
     ctx = ffi.Context(local_rank, tstream.cuda_stream)
     if args.window_bits:
@@ -211,7 +212,7 @@ def main():
             return ctx.prove_resident(r_m, s_m)
         if rank == 0:
             ctx.prove_prepare(r_m, s_m)
-        ctx.prove_shard_dev()
+        ctx.prove_shard_dev(r_m, s_m)
         ctx.copy_partial_dev(my_part.data_ptr())
         dist.all_gather_into_tensor(gather_buf.view(-1), my_part)
         if rank == 0:

@@ -65,6 +65,8 @@ int g16_ctx_create(g16_ctx** out, int device, void* main_stream) {
         delete ctx;
         return set_err(nullptr, G16_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
     }
+    // All streams share one priority: giving the main stream (witness map -> h MSM -> assembly) a higher one was measured
+    // 2 % slower on one GPU -- the side chains' latency-bound tails then pile up at the end of the proof.
     if (main_stream) {
         ctx->main = (cudaStream_t)main_stream;
         ctx->own_main = false;
@@ -77,6 +79,7 @@ int g16_ctx_create(g16_ctx** out, int device, void* main_stream) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_scale[i], cudaEventDisableTiming);
     for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev_t[i]);
     for (int i = 0; i < 10 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev_acc[i]);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_small, 4096);
@@ -121,6 +124,7 @@ void g16_ctx_destroy(g16_ctx* ctx) {
         dev_free(kv.second.coset_inv);
         dev_free(kv.second.coset_scaled);
         dev_free(kv.second.odd_scaled);
+        dev_free(kv.second.coset_inv_z);
     }
     dev_free(ctx->d_small);
     dev_free(ctx->d_partial);
@@ -130,6 +134,8 @@ void g16_ctx_destroy(g16_ctx* ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int i = 0; i < 2; i++)
+        if (ctx->ev_scale[i]) cudaEventDestroy(ctx->ev_scale[i]);
     for (int i = 0; i < 16; i++)
         if (ctx->ev_t[i]) cudaEventDestroy(ctx->ev_t[i]);
     for (int i = 0; i < 10; i++)
@@ -575,13 +581,13 @@ static int check_ready(g16_ctx* ctx) {
 }
 
 struct PartialLayout {
-    G1XYZZ h, l, a, b1;
+    G1XYZZ h, l, a, sa, rb1;
     G2XYZZ b2;
 };
 
 // Runs witness map + the five (sharded) MSMs; leaves this rank's partial sums in ctx->d_partial.  Witness must be on the
 // device (ordered on main).  Work fans out from `main` to the side streams and joins back.
-static int prove_shard_streams(g16_ctx* ctx, int reduction) {
+static int prove_shard_streams(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int reduction) {
     cudaStream_t main = ctx->main;
     PartialLayout* part = (PartialLayout*)ctx->d_partial;
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
@@ -613,6 +619,7 @@ static int prove_shard_streams(g16_ctx* ctx, int reduction) {
         chains[nchains][0] = {Q_B2, -1};
         chain_len[nchains++] = 1;
     }
+    bool scaled[2] = {false, false};
     for (int k = 0; k < nchains; k++) {
         cudaStream_t st = ctx->opt_serialize ? main : ctx->side[k];
         if (!ctx->opt_serialize) G16_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
@@ -631,12 +638,33 @@ static int prove_shard_streams(g16_ctx* ctx, int reduction) {
             }
             G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * qi], st));
             G16_TRY(msm_run(ctx, &ctx->q[qi], &ctx->scratch[qi], sc, cnt, st, ea0, ea1, from >= 0 ? &ctx->scratch[from] : nullptr));
-            void* dst = qi == Q_L ? (void*)&part->l : qi == Q_A ? (void*)&part->a : qi == Q_B1 ? (void*)&part->b1 : (void*)&part->b2;
-            size_t bytes = qi == Q_B2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
-            if (cnt && ctx->scratch[qi].result)
-                G16_CUDA(ctx, cudaMemcpyAsync(dst, ctx->scratch[qi].result, bytes, cudaMemcpyDeviceToDevice, st));
-            else
-                G16_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, st));
+            const bool have = cnt && ctx->scratch[qi].result;
+            // s * MSM_a and r * MSM_b1 are ~1.6 ms single-lane chains: they get their own streams so that neither the next
+            // MSM of this chain nor anything else waits for them; they finish beside the MSMs still in flight
+            auto scale_aside = [&](int slot, const uint64_t* k, void* dst) -> int {
+                if (!have) {
+                    G16_CUDA(ctx, cudaMemsetAsync(dst, 0, sizeof(G1XYZZ), st));
+                    return G16_OK;
+                }
+                cudaStream_t ss = ctx->opt_serialize ? st : ctx->side[5 + slot];
+                if (!ctx->opt_serialize) {
+                    G16_CUDA(ctx, cudaEventRecord(ctx->ev_scale[slot], st));
+                    G16_CUDA(ctx, cudaStreamWaitEvent(ss, ctx->ev_scale[slot], 0));
+                }
+                G16_TRY(scale_point_dev(ctx, ctx->scratch[qi].result, k, dst, ss));
+                if (!ctx->opt_serialize) G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[5 + slot], ss));
+                scaled[slot] = true;
+                return G16_OK;
+            };
+            if (qi == Q_B1) {
+                G16_TRY(scale_aside(1, r, &part->rb1));  // only r * MSM_b1 is ever needed (prover.rs:118)
+            } else {
+                void* dst = qi == Q_L ? (void*)&part->l : qi == Q_A ? (void*)&part->a : (void*)&part->b2;
+                size_t bytes = qi == Q_B2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
+                if (have) G16_CUDA(ctx, cudaMemcpyAsync(dst, ctx->scratch[qi].result, bytes, cudaMemcpyDeviceToDevice, st));
+                else G16_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, st));
+                if (qi == Q_A) G16_TRY(scale_aside(0, s, &part->sa));  // s * MSM_a for s * g_a (prover.rs:98)
+            }
             G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * qi], st));
         }
         if (!ctx->opt_serialize) G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], st));
@@ -656,8 +684,11 @@ static int prove_shard_streams(g16_ctx* ctx, int reduction) {
             G16_CUDA(ctx, cudaMemsetAsync(&part->h, 0, sizeof(G1XYZZ), main));
         G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * Q_H], main));
     }
-    if (!ctx->opt_serialize)
+    if (!ctx->opt_serialize) {
         for (int k = 0; k < nchains; k++) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[k], 0));
+        for (int k = 0; k < 2; k++)
+            if (scaled[k]) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[5 + k], 0));
+    }
     return G16_OK;
 }
 
@@ -707,15 +738,20 @@ static int prove_full(g16_ctx* ctx, const uint64_t* z, const uint64_t* r, const 
     G16_CUDA(ctx, cudaStreamWaitEvent(ctx->side[4], ctx->ev_fork, 0));
     G16_TRY(assemble_pre(ctx, r, s, ctx->side[4]));
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[4], ctx->side[4]));
-    G16_TRY(prove_shard_streams(ctx, reduction));
+    G16_TRY(prove_shard_streams(ctx, r, s, reduction));
     G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[4], 0));
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[12], main));
     g16_proof tmp;
-    int rc = assemble_proof(ctx, ctx->d_partial, 1, r, s, &tmp, main);
+    int rc = assemble_proof(ctx, ctx->d_partial, 1, &tmp, main);
     if (rc != G16_OK) return rc;
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[13], main));
     G16_CUDA(ctx, cudaStreamSynchronize(main));
     collect_timings(ctx, true);
+    {
+        float ms = -1;
+        if (cudaEventElapsedTime(&ms, ctx->ev_t[12], ctx->ev_t[15]) != cudaSuccess) cudaGetLastError();
+        ctx->tm.assemble_kernel_ms = ms;
+    }
     *out = tmp;
     return G16_OK;
 }
@@ -732,24 +768,26 @@ int g16_prove_resident(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], i
     return prove_full(ctx, nullptr, r, s, reduction, out);
 }
 
-int g16_prove_shard_dev(g16_ctx* ctx, int reduction) {
+int g16_prove_shard_dev(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], int reduction) {
     if (!ctx) return G16_ERR_BAD_ARG;
+    if (!r || !s) return set_err(ctx, G16_ERR_BAD_ARG, "prove_shard: null r/s");
     Guard g(ctx);
     G16_TRY(check_ready(ctx));
     if (!ctx->witness_resident) return set_err(ctx, G16_ERR_BAD_ARG, "prove_shard_dev: no witness uploaded");
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[14], ctx->main));
-    G16_TRY(prove_shard_streams(ctx, reduction));
+    G16_TRY(prove_shard_streams(ctx, r, s, reduction));
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[12], ctx->main));
     return G16_OK;
 }
 
-int g16_prove_shard(g16_ctx* ctx, const uint64_t* z, int reduction, g16_partial* out) {
+int g16_prove_shard(g16_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64_t s[4], int reduction, g16_partial* out) {
     if (!ctx || !out) return G16_ERR_BAD_ARG;
+    if (!r || !s) return set_err(ctx, G16_ERR_BAD_ARG, "prove_shard: null r/s");
     Guard g(ctx);
     G16_TRY(check_ready(ctx));
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[14], ctx->main));
     G16_TRY(upload_witness(ctx, z, ctx->main));
-    G16_TRY(prove_shard_streams(ctx, reduction));
+    G16_TRY(prove_shard_streams(ctx, r, s, reduction));
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[12], ctx->main));
     G16_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_partial, sizeof(g16_partial), cudaMemcpyDeviceToHost, ctx->main));
     G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
@@ -783,7 +821,7 @@ int g16_prove_combine_dev(g16_ctx* ctx, const void* dev_partials, int count, con
         G16_TRY(assemble_pre(ctx, r, s, ctx->main));
     }
     ctx->pre_pending = false;
-    return assemble_proof(ctx, dev_partials, count, r, s, out, ctx->main);
+    return assemble_proof(ctx, dev_partials, count, out, ctx->main);
 }
 
 int g16_prove_prepare(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4]) {

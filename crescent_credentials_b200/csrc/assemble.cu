@@ -7,8 +7,14 @@
 //   g_c  = s*g_a + r*g1_b - (r*s)*delta_g1 + MSM_l + MSM_h                    (:98, :118, :124-128)
 //   Proof{ a: g_a, b: g2_b, c: g_c } in affine form                          (:131-135)
 //
-// The four scalar multiplications that depend only on (r, s, pk) run in k_assemble_pre on a side stream while the
-// witness map and MSMs are in flight; k_assemble_post runs after the MSM results (summed over `count` shard partials).
+// A 254-bit scalar multiplication of a fresh point is ~4000 dependent field products: ~1.6 ms for a lone lane, which
+// would sit at the very end of the proof.  Instead the sums are split by linearity into
+//   T_a = r*delta_g1 + a_query[0] + alpha_g1,   T_b = s*delta_g1 + b_g1_query[0] + beta_g1       ((r, s, pk) only)
+//   g_a = T_a + MSM_a,        s*g_a  = s*T_a + s*MSM_a
+//   g1_b = T_b + MSM_b1,      r*g1_b = r*T_b + r*MSM_b1
+// k_assemble_pre computes T_a, s*T_a, r*T_b, rs*delta_g1 and T_b2 on a side stream at the start of the proof;
+// k_scale_point computes s*MSM_a / r*MSM_b1 (per rank, on the MSM's own stream) as soon as that MSM is done, while the
+// other MSMs are still running; k_assemble_post only adds (summing over the `count` shard partials) and normalises.
 #include "internal.cuh"
 
 namespace g16 {
@@ -18,8 +24,8 @@ struct AsmConsts {
     G2Affine beta_g2, delta_g2, b2_0;
 };
 struct AsmPre {
-    G1XYZZ r_d1, s_d1, rs_d1;
-    G2XYZZ s_d2;
+    G1XYZZ t_a, s_ta, r_tb, rs_d1;
+    G2XYZZ t_b2;
 };
 struct ProofDev {
     G1Affine a;
@@ -30,58 +36,67 @@ struct Scalar256 {
     uint32_t w[8];
 };
 
-__global__ void k_assemble_pre(AsmConsts k, Scalar256 r, Scalar256 s, Scalar256 rs, AsmPre* out) {
+__global__ void k_assemble_pre(AsmConsts k, Scalar256 r, Scalar256 s, Scalar256 rs, int r_is_zero, AsmPre* out) {
     unsigned wid = threadIdx.x >> 5;
     if (threadIdx.x & 31) return;  // no barrier in this kernel
-    if (wid == 0) out->r_d1 = scalar_mul(G1XYZZ::from_affine(k.delta_g1), r.w);
-    if (wid == 1) out->s_d1 = scalar_mul(G1XYZZ::from_affine(k.delta_g1), s.w);
+    if (wid == 0) {
+        G1XYZZ t = scalar_mul(G1XYZZ::from_affine(k.delta_g1), r.w);
+        t.madd(k.a0);
+        t.madd(k.alpha_g1);
+        out->t_a = t;
+        out->s_ta = scalar_mul(t, s.w);
+    }
+    if (wid == 1) {
+        G1XYZZ t = G1XYZZ::inf();
+        if (!r_is_zero) {  // prover.rs:102: g1_b is only computed when r != 0
+            t = scalar_mul(G1XYZZ::from_affine(k.delta_g1), s.w);
+            t.madd(k.b1_0);
+            t.madd(k.beta_g1);
+            t = scalar_mul(t, r.w);
+        }
+        out->r_tb = t;
+    }
     if (wid == 2) out->rs_d1 = scalar_mul(G1XYZZ::from_affine(k.delta_g1), rs.w);
-    if (wid == 3) out->s_d2 = scalar_mul(G2XYZZ::from_affine(k.delta_g2), s.w);
+    if (wid == 3) {
+        G2XYZZ t = scalar_mul(G2XYZZ::from_affine(k.delta_g2), s.w);
+        t.madd(k.b2_0);
+        t.madd(k.beta_g2);
+        out->t_b2 = t;
+    }
 }
 
-// partial layout (u64 words): h[16] l[16] a[16] b_g1[16] b_g2[32]  == 4 x G1XYZZ + 1 x G2XYZZ
+// out = k * in for one G1 point (one lane; latency-bound, runs beside the remaining MSMs)
+__global__ void k_scale_point(const G1XYZZ* __restrict__ in, Scalar256 k, G1XYZZ* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = scalar_mul(*in, k.w);
+}
+
+// partial layout (u64 words): h[16] l[16] a[16] s*a[16] r*b_g1[16] b_g2[32]  == 5 x G1XYZZ + 1 x G2XYZZ
 struct PartialDev {
-    G1XYZZ h, l, a, b1;
+    G1XYZZ h, l, a, sa, rb1;
     G2XYZZ b2;
 };
 static_assert(sizeof(PartialDev) == sizeof(g16_partial), "partial layout");
 
-__global__ void k_assemble_post(AsmConsts k, const AsmPre* pre, const PartialDev* parts, int count, Scalar256 r,
-                                Scalar256 s, int r_is_zero, ProofDev* out) {
-    __shared__ G1XYZZ sh_sa, sh_rb;
+__global__ void k_assemble_post(const AsmPre* pre, const PartialDev* parts, int count, ProofDev* out) {
     const unsigned wid = (threadIdx.x & 31) ? 99u : (threadIdx.x >> 5);  // one lane per warp runs a chain
     if (wid == 0) {
-        G1XYZZ ga = pre->r_d1;
-        ga.madd(k.a0);
+        G1XYZZ ga = pre->t_a;
         for (int i = 0; i < count; i++) ga.add(parts[i].a);
-        ga.madd(k.alpha_g1);
         out->a = ga.to_affine();
-        sh_sa = scalar_mul(ga, s.w);
     } else if (wid == 1) {
-        G1XYZZ gb = G1XYZZ::inf();
-        if (!r_is_zero) {
-            gb = pre->s_d1;
-            gb.madd(k.b1_0);
-            for (int i = 0; i < count; i++) gb.add(parts[i].b1);
-            gb.madd(k.beta_g1);
-            gb = scalar_mul(gb, r.w);
-        }
-        sh_rb = gb;
-    } else if (wid == 2) {
-        G2XYZZ g2 = pre->s_d2;
-        g2.madd(k.b2_0);
+        G2XYZZ g2 = pre->t_b2;
         for (int i = 0; i < count; i++) g2.add(parts[i].b2);
-        g2.madd(k.beta_g2);
         out->b = g2.to_affine();
-    }
-    // warps 0..2 finished their chains; warp 3 waits and finishes C
-    __syncthreads();
-    if (wid == 3) {
-        G1XYZZ gc = sh_sa;
-        gc.add(sh_rb);
+    } else if (wid == 2) {
+        G1XYZZ gc = pre->s_ta;
+        gc.add(pre->r_tb);
         gc.add(pre->rs_d1.neg());
-        for (int i = 0; i < count; i++) gc.add(parts[i].l);
-        for (int i = 0; i < count; i++) gc.add(parts[i].h);
+        for (int i = 0; i < count; i++) {
+            gc.add(parts[i].sa);
+            gc.add(parts[i].rb1);
+            gc.add(parts[i].l);
+            gc.add(parts[i].h);
+        }
         out->c = gc.to_affine();
     }
 }
@@ -126,15 +141,19 @@ static void* affine_ptr(g16_ctx* ctx) { return (char*)ctx->d_small + 2048; }
 int assemble_pre(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, cudaStream_t st) {
     Fr rm = fr_load(r), sm = fr_load(s);
     Fr rs = rm * sm;
-    G16_LAUNCH(ctx, k_assemble_pre, 1, 128, 0, st, consts_of(ctx), canon(rm), canon(sm), canon(rs), pre_ptr(ctx));
+    G16_LAUNCH(ctx, k_assemble_pre, 1, 128, 0, st, consts_of(ctx), canon(rm), canon(sm), canon(rs), (int)rm.is_zero(), pre_ptr(ctx));
     return G16_OK;
 }
 
-int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, const uint64_t* r, const uint64_t* s, g16_proof* out,
-                   cudaStream_t st) {
-    Fr rm = fr_load(r), sm = fr_load(s);
-    G16_LAUNCH(ctx, k_assemble_post, 1, 128, 0, st, consts_of(ctx), (const AsmPre*)pre_ptr(ctx),
-               (const PartialDev*)partials_dev, count, canon(rm), canon(sm), (int)rm.is_zero(), proof_ptr(ctx));
+int scale_point_dev(g16_ctx* ctx, const void* in_xyzz, const uint64_t* k_mont, void* out_xyzz, cudaStream_t st) {
+    G16_LAUNCH(ctx, k_scale_point, 1, 32, 0, st, (const G1XYZZ*)in_xyzz, canon(fr_load(k_mont)), (G1XYZZ*)out_xyzz);
+    return G16_OK;
+}
+
+int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, g16_proof* out, cudaStream_t st) {
+    G16_LAUNCH(ctx, k_assemble_post, 1, 128, 0, st, (const AsmPre*)pre_ptr(ctx), (const PartialDev*)partials_dev, count,
+               proof_ptr(ctx));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[15], st));
     ProofDev host;
     G16_CUDA(ctx, cudaMemcpyAsync(&host, proof_ptr(ctx), sizeof(ProofDev), cudaMemcpyDeviceToHost, st));
     G16_CUDA(ctx, cudaStreamSynchronize(st));

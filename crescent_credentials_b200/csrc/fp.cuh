@@ -574,6 +574,10 @@ struct Fq2 {
         Fq n = (c0.sqr() + c1.sqr()).inverse();
         return Fq2{c0 * n, (c1 * n).neg()};
     }
+    G16_HD_NOINLINE Fq2 inverse_bgcd() const {  // same value, low-latency Fq inversion
+        Fq n = (c0.sqr() + c1.sqr()).inverse_bgcd();
+        return Fq2{c0 * n, (c1 * n).neg()};
+    }
 };
 
 }  // namespace g16

@@ -14,7 +14,7 @@
 
 namespace g16 {
 
-constexpr int kSideStreams = 5;
+constexpr int kSideStreams = 7;  // 0-3 MSM chains, 4 (r, s)-only scalar multiplications, 5-6 s*MSM_a / r*MSM_b1
 constexpr int kMsmSlots = 8;
 constexpr int kNumSMs = 148;  // B200
 
@@ -30,6 +30,8 @@ struct NttTables {
     bool zinv_ok = false;
     Fr* coset_scaled = nullptr;  // g^i / n                    (iNTT's 1/n folded into the following coset NTT)
     Fr* odd_scaled = nullptr;    // omega_2n^i / n, i < n      (CircomReduction coset: qap.rs:63-72, same folding)
+    Fr* coset_inv_z = nullptr;   // g^-i / (n (g^n - 1))        (coset iNTT post-scale with the division by Z folded in)
+    Fr zinv_n;                   // 1 / (n (g^n - 1))
 };
 
 // ---- MSM engine state for one set of bases -------------------------------------------------------------------------
@@ -93,6 +95,7 @@ struct g16_ctx {
     bool own_main = false;
     cudaStream_t side[g16::kSideStreams] = {};
     cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_scale[2] = {};
     cudaEvent_t ev_join[g16::kSideStreams] = {};
     cudaEvent_t ev_t[16] = {};
     std::mutex mu;
@@ -181,8 +184,10 @@ int ntt_get_tables(g16_ctx* ctx, unsigned log_n, NttTables** out);
 // pre (dif) / post (dit) are optional element-wise scale tables indexed by the natural index; post_scalar (dit) is an
 // optional uniform Montgomery factor.
 int ntt_dif(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* pre, cudaStream_t st);
+// pre_mul (dit): optional vector multiplied in element-wise on the first load (same physical order as data);
+// post_sub (dit, with post): optional vector subtracted after the post scaling (natural order).
 int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* post, const Fr* post_scalar,
-            cudaStream_t st);
+            cudaStream_t st, const Fr* pre_mul = nullptr, const Fr* post_sub = nullptr);
 int bitrev_permute(g16_ctx* ctx, Fr* data, unsigned log_n, cudaStream_t st);
 int pow_table_dev(g16_ctx* ctx, Fr* out, size_t n, Fr base, Fr scale, cudaStream_t st);
 int ntt_api(g16_ctx* ctx, Fr* data_dev, unsigned log_n, int inverse, int coset, cudaStream_t st);
@@ -210,8 +215,9 @@ int fixed_base_dev(g16_ctx* ctx, int group, const Fr* scalars_dev, size_t n, voi
 int assemble_pre(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, cudaStream_t st);
 G1Affine g1_generator();
 G2Affine g2_generator();
-int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, const uint64_t* r, const uint64_t* s,
-                   g16_proof* out, cudaStream_t st);
+// out = k * in for one G1 XYZZ point on the device (k: Montgomery Fr on the host)
+int scale_point_dev(g16_ctx* ctx, const void* in_xyzz, const uint64_t* k_mont, void* out_xyzz, cudaStream_t st);
+int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, g16_proof* out, cudaStream_t st);
 int xyzz_to_affine_host(g16_ctx* ctx, int group, const void* xyzz_dev, uint64_t* out, int* out_inf, cudaStream_t st);
 
 }  // namespace g16

@@ -111,6 +111,8 @@ int ntt_get_tables(g16_ctx* ctx, unsigned log_n, NttTables** out) {
     G16_TRY(make_pow_table(ctx, &t.coset_inv, n, gi, t.n_inv, ctx->main));
     G16_TRY(make_pow_table(ctx, &t.coset_scaled, n, g, t.n_inv, ctx->main));
     if (log_n < 28) G16_TRY(make_pow_table(ctx, &t.odd_scaled, n, fr_omega(log_n + 1), t.n_inv, ctx->main));
+    t.zinv_n = t.zinv * t.n_inv;
+    if (t.zinv_ok) G16_TRY(make_pow_table(ctx, &t.coset_inv_z, n, gi, t.zinv_n, ctx->main));
     G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
     auto res = ctx->ntt.emplace(log_n, t);
     *out = &res.first->second;
@@ -124,7 +126,7 @@ template <bool DIT>
 __global__ void __launch_bounds__(kNttThreads, 2)
     k_ntt_pass(Fr* __restrict__ data, const Fr* __restrict__ tw, unsigned log_n, unsigned s_lo, unsigned nlev,
                unsigned t_log, const Fr* __restrict__ pre, const Fr* __restrict__ post, Fr post_scalar,
-               int has_post_scalar) {
+               int has_post_scalar, const Fr* __restrict__ sub) {
     extern __shared__ uint4 smem[];
     const unsigned tile_log = nlev + t_log;
     const unsigned tile = 1u << tile_log;
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(kNttThreads, 2)
             *reinterpret_cast<uint4*>(&x.v[0]) = a;
             *reinterpret_cast<uint4*>(&x.v[4]) = b;
             x = x * (post ? post[gi] : post_scalar);
+            if (sub) x = x - sub[gi];
             a = *reinterpret_cast<uint4*>(&x.v[0]);
             b = *reinterpret_cast<uint4*>(&x.v[4]);
         }
@@ -210,9 +213,16 @@ __global__ void __launch_bounds__(kNttThreads, 2)
     }
 }
 
-__global__ void k_scale_table(Fr* __restrict__ data, const Fr* __restrict__ tbl, Fr scalar, int use_tbl, size_t n) {
+// the element-wise part of a transform when there is no butterfly to ride on (n == 1)
+__global__ void k_scale_table(Fr* __restrict__ data, const Fr* __restrict__ pre, const Fr* __restrict__ tbl, Fr scalar,
+                              int scale, const Fr* __restrict__ sub, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) data[i] = data[i] * (use_tbl ? tbl[i] : scalar);
+    if (i >= n) return;
+    Fr x = data[i];
+    if (pre) x = x * pre[i];
+    if (scale) x = x * (tbl ? tbl[i] : scalar);
+    if (sub) x = x - sub[i];
+    data[i] = x;
 }
 
 struct Pass {
@@ -253,13 +263,14 @@ static int ensure_smem_attr(g16_ctx* ctx) {
 }
 
 int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* post, const Fr* post_scalar,
-            cudaStream_t st) {
+            cudaStream_t st, const Fr* pre_mul, const Fr* post_sub) {
+    if (post_sub && !post) return set_err(ctx, G16_ERR_BAD_ARG, "ntt_dit: post_sub needs a post table");
     G16_TRY(ensure_smem_attr(ctx));
     auto passes = plan_passes(t->log_n);
     const Fr* tw = inverse_root ? t->tw_inv : t->tw;
     Fr ps = post_scalar ? *post_scalar : Fr::zero();
-    if (passes.empty()) {  // n == 1: only the scaling remains
-        if (post || post_scalar) G16_LAUNCH(ctx, k_scale_table, 1, 32, 0, st, data, post, ps, (int)(post != nullptr), (size_t)1);
+    if (passes.empty()) {  // n == 1: only the element-wise work remains
+        G16_LAUNCH(ctx, k_scale_table, 1, 32, 0, st, data, pre_mul, post, ps, (int)(post != nullptr || post_scalar != nullptr), post_sub, (size_t)1);
         return G16_OK;
     }
     for (size_t k = 0; k < passes.size(); k++) {
@@ -268,8 +279,8 @@ int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* p
         size_t blocks = ((size_t)1 << t->log_n) >> (p.nlev + p.t_log);
         size_t smem = ((size_t)1 << (p.nlev + p.t_log)) * 32;
         G16_LAUNCH(ctx, k_ntt_pass<true>, (unsigned)blocks, kNttThreads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
-                   p.t_log, (const Fr*)nullptr, last ? post : (const Fr*)nullptr, ps,
-                   (int)(last && post_scalar != nullptr && post == nullptr));
+                   p.t_log, k == 0 ? pre_mul : (const Fr*)nullptr, last ? post : (const Fr*)nullptr, ps,
+                   (int)(last && post_scalar != nullptr && post == nullptr), last ? post_sub : (const Fr*)nullptr);
     }
     return G16_OK;
 }
@@ -284,7 +295,7 @@ int ntt_dif(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* p
         size_t blocks = ((size_t)1 << t->log_n) >> (p.nlev + p.t_log);
         size_t smem = ((size_t)1 << (p.nlev + p.t_log)) * 32;
         G16_LAUNCH(ctx, k_ntt_pass<false>, (unsigned)blocks, kNttThreads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
-                   p.t_log, first ? pre : (const Fr*)nullptr, (const Fr*)nullptr, Fr::zero(), 0);
+                   p.t_log, first ? pre : (const Fr*)nullptr, (const Fr*)nullptr, Fr::zero(), 0, (const Fr*)nullptr);
     }
     return G16_OK;
 }

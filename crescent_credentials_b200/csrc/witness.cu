@@ -51,13 +51,6 @@ __global__ void k_place_inputs(const Fr* __restrict__ z, Fr* __restrict__ a, uin
     st_fr(a + o, ld_fr(z + i));
 }
 
-// a = (a*b - c) * zinv       (r1cs_to_qap.rs:187,205-208)
-__global__ void k_quotient(Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c, Fr zinv, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr x = ld_fr(a + i) * ld_fr(b + i) - ld_fr(c + i);
-    st_fr(a + i, x * zinv);
-}
 // c = a*b  (qap.rs:52-58) ;  a = a*b - c (qap.rs:74-88)
 __global__ void k_mul_into(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ c, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,16 +92,19 @@ int witness_map_dev(g16_ctx* ctx, int reduction, cudaStream_t st) {
         if (!t->zinv_ok) return set_err(ctx, G16_ERR_VANISHING_ZERO, "g^n - 1 == 0");
         G16_TRY(r1cs_eval_dev(ctx, a, b, c, true, st));
         G16_LAUNCH(ctx, k_place_inputs, (unsigned)((ctx->ni + 127) / 128), 128, 0, st, ctx->d_z, a, ctx->nc, ctx->ni, lr);
-        // iNTT (1/n deferred into the coset table) -> coset NTT; evaluations come out bit-reversed in all three
+        // The reference runs seven transforms: iFFT and coset FFT of a, b and c, the pointwise (a*b - c) / Z, one coset
+        // iFFT (r1cs_to_qap.rs:179-210).  Z is CONSTANT on the coset (Z(g w^i) = g^n - 1), so by linearity
+        //     h = coset_iFFT((A'*B' - C') / Z) = (coset_iFFT(A'*B') - iFFT(c)) / (g^n - 1)
+        // as exact field identities, whatever the witness: c needs ONE transform, and the quotient kernel disappears.
+        //   a, b: iNTT (1/n deferred into the coset table) -> coset NTT, evaluations bit-reversed
         G16_TRY(ntt_dit(ctx, a, t, true, nullptr, nullptr, st));
         G16_TRY(ntt_dit(ctx, b, t, true, nullptr, nullptr, st));
-        G16_TRY(ntt_dit(ctx, c, t, true, nullptr, nullptr, st));
         G16_TRY(ntt_dif(ctx, a, t, false, t->coset_scaled, st));
         G16_TRY(ntt_dif(ctx, b, t, false, t->coset_scaled, st));
-        G16_TRY(ntt_dif(ctx, c, t, false, t->coset_scaled, st));
-        G16_LAUNCH(ctx, k_quotient, eb, 256, 0, st, a, b, c, t->zinv, n);
-        // coset iNTT back to coefficients, natural order
-        G16_TRY(ntt_dit(ctx, a, t, true, t->coset_inv, nullptr, st));
+        //   c: coefficients / (g^n - 1), natural order
+        G16_TRY(ntt_dit(ctx, c, t, true, nullptr, &t->zinv_n, st));
+        //   coset iNTT of a*b (product taken on the first load; g^-i / (n (g^n - 1)) and the subtraction on the last store)
+        G16_TRY(ntt_dit(ctx, a, t, true, t->coset_inv_z, nullptr, st, b, c));
     } else if (reduction == G16_REDUCTION_CIRCOM) {
         if (ctx->log_n >= 28) return set_err(ctx, G16_ERR_DEGREE_TOO_LARGE, "circom reduction needs a 2n domain");
         G16_TRY(r1cs_eval_dev(ctx, a, b, nullptr, true, st));

@@ -17,7 +17,7 @@ REDUCTION_LIBSNARK, REDUCTION_CIRCOM = 0, 1
 ENC_MONTGOMERY, ENC_CANONICAL = 0, 1
 FIELD_FR, FIELD_FQ, FIELD_FQ2 = 0, 1, 2
 OP_MUL, OP_ADD, OP_SUB, OP_NEG, OP_INV, OP_TO_MONT, OP_FROM_MONT, OP_SQR, OP_MUL_BCAST, OP_ADD_BCAST = range(10)
-PARTIAL_U64 = 4 * 16 + 32
+PARTIAL_U64 = 5 * 16 + 32
 
 # every symbol include/g16_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -66,11 +66,12 @@ class Partial(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "witness_map_ms", "msm_h_ms", "msm_l_ms", "msm_a_ms",
                                          "msm_b_g1_ms", "msm_b_g2_ms", "assemble_ms", "total_ms")] + [
-        ("acc_ms", C.c_float * 5), ("_reserved", C.c_float * 3)]
+        ("acc_ms", C.c_float * 5), ("assemble_kernel_ms", C.c_float), ("_reserved", C.c_float * 2)]
 
     def as_dict(self):
         d = {n: float(getattr(self, n)) for n, _ in self._fields_[:9]}
         d["acc_ms"] = dict(zip(("h", "l", "a", "b_g1", "b_g2"), (float(x) for x in self.acc_ms)))
+        d["assemble_kernel_ms"] = float(self.assemble_kernel_ms)
         return d
 
 
@@ -109,10 +110,10 @@ def load_library() -> C.CDLL:
     lib.g16_prove.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ProofOut)]
     lib.g16_upload_witness.argtypes = [C.c_void_p, C.c_void_p]
     lib.g16_prove_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ProofOut)]
-    lib.g16_prove_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Partial)]
+    lib.g16_prove_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Partial)]
     lib.g16_prove_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
     lib.g16_partial_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
-    lib.g16_prove_shard_dev.argtypes = [C.c_void_p, C.c_int]
+    lib.g16_prove_shard_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.g16_copy_partial_dev.argtypes = [C.c_void_p, C.c_void_p]
     lib.g16_prove_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.g16_prove_combine_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
@@ -333,15 +334,19 @@ class Context:
         self.check(self.lib.g16_prove_resident(self.h, _ptr(r), _ptr(s), reduction, C.byref(out)))
         return out
 
-    def prove_shard(self, z, reduction=REDUCTION_LIBSNARK) -> np.ndarray:
+    def prove_shard(self, z, r, s, reduction=REDUCTION_LIBSNARK) -> np.ndarray:
         if isinstance(z, np.ndarray):
             z = np.ascontiguousarray(z, dtype=np.uint64)
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
         p = Partial()
-        self.check(self.lib.g16_prove_shard(self.h, _ptr(z), reduction, C.byref(p)))
+        self.check(self.lib.g16_prove_shard(self.h, _ptr(z), _ptr(r), _ptr(s), reduction, C.byref(p)))
         return np.frombuffer(bytes(p), dtype=np.uint64).copy()
 
-    def prove_shard_dev(self, reduction=REDUCTION_LIBSNARK):
-        self.check(self.lib.g16_prove_shard_dev(self.h, reduction))
+    def prove_shard_dev(self, r, s, reduction=REDUCTION_LIBSNARK):
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        self.check(self.lib.g16_prove_shard_dev(self.h, _ptr(r), _ptr(s), reduction))
 
     def prove_prepare(self, r, s):
         r = np.ascontiguousarray(r, dtype=np.uint64)

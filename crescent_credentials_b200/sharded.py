@@ -48,7 +48,7 @@ class ShardedProver:
         self.ctx.upload_witness(z_mont)
         if self.rank == 0:
             self.ctx.prove_prepare(rr, ss)   # overlaps r*delta, s*delta, ... with the shard MSMs
-        self.ctx.prove_shard_dev(reduction)
+        self.ctx.prove_shard_dev(rr, ss, reduction)
         self.ctx.copy_partial_dev(self.mine.data_ptr())
         allp = gather_partials(self.mine, self.world)
         if self.rank != 0:

@@ -100,8 +100,10 @@ typedef struct g16_proof {
     int32_t _pad;
 } g16_proof;
 
-/* Per-rank partial results of the five sharded MSMs (XYZZ, Montgomery): h, l, a, b_g1 (16 x u64 each), b_g2 (32 x u64). */
-#define G16_PARTIAL_U64 (4 * 16 + 32)
+/* Per-rank partial results of the five sharded MSMs (XYZZ, Montgomery): h, l, a, s*a, r*b_g1 (16 x u64 each), b_g2
+ * (32 x u64).  Every rank scales its own a / b_g1 partial by s / r while its other MSMs are still running, so that the
+ * combine step only adds (s*g_a and r*g1_b of prover.rs:98,118 by linearity). */
+#define G16_PARTIAL_U64 (5 * 16 + 32)
 typedef struct g16_partial {
     uint64_t w[G16_PARTIAL_U64];
 } g16_partial;
@@ -116,7 +118,8 @@ typedef struct g16_timings {
     float total_ms;       /* "Groth16::Prover" */
     /* with option "kernel_events": duration of the bucket-accumulation kernel of each MSM (h, l, a, b_g1, b_g2) */
     float acc_ms[5];
-    float _reserved[3];
+    float assemble_kernel_ms; /* k_assemble_post alone (assemble_ms also covers the proof read-back) */
+    float _reserved[2];
 } g16_timings;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------------- */
@@ -144,14 +147,14 @@ int g16_prove(g16_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64
 int g16_upload_witness(g16_ctx* ctx, const uint64_t* z);
 int g16_prove_resident(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], int reduction, g16_proof* out);
 
-/* MSM-sharded proving: every rank calls g16_prove_shard on its context (loaded with its shard), the G partials are
- * gathered (one small NCCL gather by the host glue) and rank 0 calls g16_prove_combine. */
-int g16_prove_shard(g16_ctx* ctx, const uint64_t* z, int reduction, g16_partial* out);
+/* MSM-sharded proving: every rank calls g16_prove_shard on its context (loaded with its shard) with the same (r, s), the
+ * G partials are gathered (one small NCCL gather by the host glue) and rank 0 calls g16_prove_combine. */
+int g16_prove_shard(g16_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64_t s[4], int reduction, g16_partial* out);
 int g16_prove_combine(g16_ctx* ctx, const g16_partial* partials, int count, const uint64_t r[4], const uint64_t s[4],
                       g16_proof* out);
 /* Device pointer + byte size of this context's partial buffer, for a device-side NCCL gather. */
 int g16_partial_dev(g16_ctx* ctx, void** dev_ptr, size_t* bytes);
-int g16_prove_shard_dev(g16_ctx* ctx, int reduction);          /* witness resident; result left in the device partial */
+int g16_prove_shard_dev(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], int reduction); /* witness resident; result left in the device partial */
 int g16_copy_partial_dev(g16_ctx* ctx, void* dst_dev);         /* stream-ordered D2D copy of the partial (e.g. into an NCCL buffer) */
 /* Optional, rank 0: starts the (r, s, pk)-only scalar multiplications on a side stream so that they overlap the shard work;
  * a later g16_prove_combine[_dev] with the same (r, s) joins them instead of running them serially. */

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(ffi.ProofOut) == 8 * 8 + 16 * 8 + 8 * 8 + 16
-    assert ctypes.sizeof(ffi.Partial) == ffi.PARTIAL_U64 * 8 == 768
+    assert ctypes.sizeof(ffi.Partial) == ffi.PARTIAL_U64 * 8 == 896
     assert ctypes.sizeof(ffi.Timings) == 17 * 4
 
 

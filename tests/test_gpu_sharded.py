@@ -25,8 +25,9 @@ def test_sharded_prove_matches_golden(name, world):
             ctxs.append(ctx)
             ctx.load_r1cs(mats.num_constraints, mats.num_instance_variables, wires, mats.row_ptr, mats.col, mats.val, mats.encoding)
             ctx.load_pk(pk.arrays, pk.encoding, rank, world)
-            parts.append(ctx.prove_shard(z))
         r, s = g.fr_to_mont([int(meta["r"], 16)])[0], g.fr_to_mont([int(meta["s"], 16)])[0]
+        for ctx in ctxs:
+            parts.append(ctx.prove_shard(z, r, s))
         proof = g.Proof.from_ffi(ctxs[0].prove_combine(np.stack(parts), r, s))
         assert proof.serialize_uncompressed().hex() == meta["proof_uncompressed"]
         with pytest.raises(ffi.G16Error):   # a sharded context refuses the single-GPU entry point
