@@ -2,6 +2,7 @@
 // stream fork/join of the witness map, the five MSMs and the assembly, mirroring
 // Groth16::create_proof_with_reduction_and_matrices (forks/groth16/src/prover.rs:26-51).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "internal.cuh"

@@ -164,24 +164,33 @@ __global__ void __launch_bounds__(kRsThreads)
     for (unsigned b = threadIdx.x; b < NB; b += kRsThreads) hist[((size_t)seg * NB + b) * tiles_per_seg + tile] = sh[b];
 }
 
-// Warp w owns items [w*512, (w+1)*512) of the tile as 16 rows of 32: ranking order == index order (stable).  Only the
-// keys and the packed ranks stay in registers across the barriers (values are loaded when their position is known), so
-// that four blocks fit an SM.
+// Scatter of one tile.  Warp w owns items [w*512, (w+1)*512) of the tile as 16 rows of 32, so ranking order == index
+// order (stable).  The tile is first sorted by digit INTO SHARED MEMORY and then written out in that order: the items of
+// a bin leave as one contiguous run, so a warp's store touches a handful of 32-byte sectors instead of 32 (the direct
+// scatter was bound by L2 sector writes carrying 4 useful bytes each).
 template <unsigned BITS>
-__global__ void __launch_bounds__(kRsThreads, 4)
+__global__ void __launch_bounds__(kRsThreads, 3)
     k_rs_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t* __restrict__ okeys,
                  uint32_t* __restrict__ ovals, size_t seg_len, unsigned tiles_per_seg, unsigned shift,
                  const uint32_t* __restrict__ hist) {
     constexpr unsigned NB = 1u << BITS;
     constexpr unsigned NW = kRsThreads / 32;
-    extern __shared__ uint32_t wcnt[];  // [NW][NB]
+    constexpr unsigned BPT = NB / kRsThreads;  // bins per thread in the prefix step (NB >= 256)
+    extern __shared__ uint32_t smem[];
+    uint32_t* wcnt = smem;                 // [NW][NB] per-warp bin counts, then per-warp local offsets
+    uint32_t* local_off = wcnt + NW * NB;  // [NB] first tile-local slot of every bin
+    uint32_t* gbase = local_off + NB;      // [NB] first global slot of this tile's items of every bin
+    uint32_t* skey = gbase + NB;           // [kRsTile] the tile sorted by digit
+    uint32_t* sval = skey + kRsTile;
+    __shared__ uint32_t scan_sh[33];
     unsigned seg = blockIdx.x / tiles_per_seg, tile = blockIdx.x % tiles_per_seg;
     unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (unsigned i = threadIdx.x; i < NW * NB; i += kRsThreads) wcnt[i] = 0;
     __syncthreads();
     uint32_t* mine = wcnt + wid * NB;
     size_t seg_base = (size_t)seg * seg_len;
-    size_t lo = (size_t)tile * kRsTile + (size_t)wid * (32 * kRsItems);
+    size_t tile_lo = (size_t)tile * kRsTile;
+    size_t lo = tile_lo + (size_t)wid * (32 * kRsItems);
     uint32_t k[kRsItems];
     uint32_t packed[kRsItems];  // rank within the row's digit group | group size << 8 | leader << 16 | valid << 17
 #pragma unroll
@@ -203,13 +212,34 @@ __global__ void __launch_bounds__(kRsThreads, 4)
         __syncwarp();
     }
     __syncthreads();
-    for (unsigned bin = threadIdx.x; bin < NB; bin += kRsThreads) {
-        uint32_t run = hist[((size_t)seg * NB + bin) * tiles_per_seg + tile];
+    // bins [BPT*t, BPT*(t+1)) belong to thread t: bin totals -> exclusive scan over the bins -> per-warp offsets
+    {
+        uint32_t tot[BPT];
+        uint32_t tsum = 0;
 #pragma unroll
-        for (unsigned w = 0; w < NW; w++) {
-            uint32_t t = wcnt[w * NB + bin];
-            wcnt[w * NB + bin] = run;
-            run += t;
+        for (unsigned j = 0; j < BPT; j++) {
+            unsigned bin = threadIdx.x * BPT + j;
+            uint32_t t = 0;
+#pragma unroll
+            for (unsigned w = 0; w < NW; w++) t += wcnt[w * NB + bin];
+            tot[j] = t;
+            tsum += t;
+        }
+        uint32_t dummy;
+        uint32_t run = block_exclusive_scan(tsum, &dummy, scan_sh);
+#pragma unroll
+        for (unsigned j = 0; j < BPT; j++) {
+            unsigned bin = threadIdx.x * BPT + j;
+            local_off[bin] = run;
+            gbase[bin] = hist[((size_t)seg * NB + bin) * tiles_per_seg + tile];
+            uint32_t o = run;
+#pragma unroll
+            for (unsigned w = 0; w < NW; w++) {
+                uint32_t t = wcnt[w * NB + bin];
+                wcnt[w * NB + bin] = o;
+                o += t;
+            }
+            run += tot[j];
         }
     }
     __syncthreads();
@@ -225,9 +255,19 @@ __global__ void __launch_bounds__(kRsThreads, 4)
         if (packed[r] & 0x10000u) mine[d] += (packed[r] >> 8) & 0xffu;
         __syncwarp();
         if (valid) {
-            okeys[pos] = k[r];
-            ovals[pos] = v;
+            skey[pos] = k[r];
+            sval[pos] = v;
         }
+    }
+    __syncthreads();
+    size_t left = seg_len - tile_lo;
+    unsigned count = left < (size_t)kRsTile ? (unsigned)left : (unsigned)kRsTile;
+    for (unsigned i = threadIdx.x; i < count; i += kRsThreads) {
+        uint32_t key = skey[i];
+        uint32_t d = (key >> shift) & (NB - 1);
+        uint32_t dst = gbase[d] + (i - local_off[d]);
+        okeys[dst] = key;
+        ovals[dst] = sval[i];
     }
 }
 
@@ -235,7 +275,7 @@ template <unsigned BITS>
 static int radix_pass(g16_ctx* ctx, const uint32_t* keys, const uint32_t* vals, uint32_t* okeys, uint32_t* ovals, size_t seg_len,
                       unsigned nseg, unsigned tiles, unsigned shift, uint32_t* hist, uint32_t* scan_tmp, cudaStream_t st) {
     constexpr unsigned NB = 1u << BITS;
-    const size_t smem = (size_t)(kRsThreads / 32) * NB * sizeof(uint32_t);
+    const size_t smem = ((size_t)(kRsThreads / 32) * NB + 2 * NB + 2 * kRsTile) * sizeof(uint32_t);
     static bool attr_done = false;
     if (!attr_done && smem > 48 * 1024) {
         G16_CUDA(ctx, cudaFuncSetAttribute(k_rs_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

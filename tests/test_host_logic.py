@@ -127,3 +127,59 @@ def test_sharded_msm_partials_add_up_on_cpu():
         lo, hi = shard_range(97, r, 4)
         acc = o.G1.add(acc, g.g1_from_mont(c.msm(1, pts[lo:hi], sc[lo:hi])))
     assert acc == full
+
+
+# ---- rand 0.8 StdRng mirror (crescent_credentials_b200/rng.py) ---------------------------------------------------------
+def test_chacha_block_rfc8439_vector():
+    """RFC 8439 section 2.3.2 (20 rounds) pins the quarter round and the column/diagonal schedule."""
+    import struct
+    from crescent_credentials_b200 import rng
+    key = list(struct.unpack("<8I", bytes(range(32))))
+    out = rng.chacha_block(list(rng._SIGMA) + key + [1, 0x09000000, 0x4A000000, 0], 20)
+    assert out == [0xE4E7F110, 0x15593BD1, 0x1FDD0F50, 0xC47120A3, 0xC7F4D1C7, 0x0368C033, 0x9AAA2204, 0x4E6CD4C3,
+                   0x466482D2, 0x09AA9F07, 0x05D7C214, 0xA2028BD9, 0xD19C12B5, 0xB94E16DE, 0xE883D0CB, 0x4E3C50A2]
+
+
+def test_chacha12_zero_key_keystream():
+    """ChaCha12, 256-bit zero key, zero IV, block 0 (eSTREAM test vector TC1): the 12-round StdRng core."""
+    import struct
+    from crescent_credentials_b200 import rng
+    r = rng.StdRng(bytes(32))
+    ks = b"".join(struct.pack("<I", r.next_u32()) for _ in range(16))
+    assert ks.hex() == ("9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"
+                        "0564f879d27ae3c02ce82834acfa8c793a629f2ca0de6919610be82f411326be")
+
+
+def test_stdrng_word_order_and_buffer_straddle():
+    from crescent_credentials_b200 import rng
+    a, b = rng.test_rng(), rng.test_rng()
+    words = [a.next_u32() for _ in range(140)]
+    # next_u64 = (low word first) pairs of the same stream
+    assert [b.next_u64() for _ in range(3)] == [words[2 * i] | (words[2 * i + 1] << 32) for i in range(3)]
+    # BlockRng rule at the end of the 64-word buffer: the last word is the low half, the next buffer's first the high half
+    c = rng.test_rng()
+    for _ in range(63):
+        c.next_u32()
+    assert c.next_u64() == words[63] | (words[64] << 32)
+    assert c.next_u32() == words[65]
+    # the 64-bit block counter keeps running across buffers (words 64.. come from blocks 4..7)
+    d = rng.test_rng()
+    for _ in range(64):
+        d.next_u32()
+    assert d.counter == 4 and d.next_u64() == words[64] | (words[65] << 32)
+    assert rng.StdRng.seed_from_u64(42).next_u64() == rng.StdRng.seed_from_u64(42).next_u64()
+    assert rng.StdRng.seed_from_u64(42).next_u64() != rng.StdRng.seed_from_u64(43).next_u64()
+
+
+def test_sample_fr_with_stdrng_follows_fr_rand():
+    """Fr::rand (ark-ff 0.4): 4 x next_u64 limb 0 first, top limb masked to 254 bits, reject >= r, accepted integer is the
+    Montgomery representation."""
+    from crescent_credentials_b200 import rng
+    a, b = rng.test_rng(), rng.test_rng()
+    got = [g.sample_fr(a) for _ in range(6)]
+    want = []
+    while len(want) < 6:
+        v = sum(b.next_u64() << (64 * k) for k in range(4)) & ((1 << 254) - 1)
+        if v < o.R_MOD:
+            want.append(v * pow(1 << 256, -1, o.R_MOD) % o.R_MOD)
+    assert got == want and len(set(got)) == 6
