@@ -886,6 +886,34 @@ int g16_pow_table(g16_ctx* ctx, const uint64_t base[4], const uint64_t scale[4],
     return rc;
 }
 
+int g16_get_msm_stats(g16_ctx* ctx, int which, uint64_t* out, int capacity) {
+    if (!ctx || !out || which < 0 || which > 4 || capacity < 16) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "msm_stats: bad argument") : G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!ctx->have_pk) return set_err(ctx, G16_ERR_BAD_ARG, "msm_stats: no proving key loaded");
+    int owner = which;
+    if (which == Q_L && ctx->share_al) owner = Q_A;
+    if (which == Q_B2 && ctx->share_b) owner = Q_B1;
+    const MsmBases& mb = ctx->q[which];
+    const MsmScratch& dg = ctx->scratch[owner];
+    G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    memset(out, 0, sizeof(uint64_t) * (size_t)capacity);
+    out[0] = mb.n;
+    out[1] = (uint64_t)mb.c;
+    out[2] = (uint64_t)mb.windows;
+    out[3] = (uint64_t)mb.ba_levels;
+    out[4] = dg.cap_buckets;
+    out[5] = owner != which;  // digit stage shared with another MSM
+    if (mb.n == 0) return G16_OK;
+    uint32_t v = 0;
+    for (int k = 1; k <= mb.ba_levels && 7 + k < capacity; k++) {
+        G16_CUDA(ctx, cudaMemcpy(&v, dg.ba_lvl + (size_t)k * dg.ba_stride + dg.cap_buckets, 4, cudaMemcpyDeviceToHost));
+        out[7 + k] = v;  // points left after level k == output slots of level k
+    }
+    G16_CUDA(ctx, cudaMemcpy(&v, dg.counters, 4, cudaMemcpyDeviceToHost));
+    out[6] = v;  // XYZZ tasks of the tail
+    return G16_OK;
+}
+
 int g16_get_timings(g16_ctx* ctx, g16_timings* out) {
     if (!ctx || !out) return G16_ERR_BAD_ARG;
     *out = ctx->tm;

@@ -519,10 +519,12 @@ static int msm_point_stage(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Msm
     const size_t tcap = task_capacity(items, nbuckets, L);
     const uint32_t* t_start = dg->tasks;
     const uint32_t* t_len = dg->tasks + dg->cap_tasks;
-    if (ev0) G16_CUDA(ctx, cudaEventRecord(ev0, st));
+    // kernel_events == 1: the events bracket the whole bucket accumulation (steps 6-7); == 2: only the first level's k_ba_add
+    const bool one_kernel = ctx->opt_kernel_events == 2 && L > 0;
+    if (ev0 && !one_kernel) G16_CUDA(ctx, cudaEventRecord(ev0, st));
     // 6. batched-affine levels
     const void* pts = mb->pts;
-    if (L) G16_TRY(ba_run_levels(ctx, mb, sc, dg, items, nbuckets, L, &pts, st));
+    if (L) G16_TRY(ba_run_levels(ctx, mb, sc, dg, items, nbuckets, L, &pts, st, one_kernel ? ev0 : nullptr, one_kernel ? ev1 : nullptr));
     // 7. accumulate the survivors
     {
         size_t want = (tcap + 127) / 128;
@@ -536,7 +538,7 @@ static int msm_point_stage(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Msm
             G16_LAUNCH(ctx, (k_accumulate<F, 3, false>), grid, 128, 0, st, (const Affine<F>*)pts, dg->s_vals, dg->s_tkeys, dg->s_tvals,
                        t_start, t_len, (XYZZ<F>*)sc->partial, tcap);
     }
-    if (ev1) G16_CUDA(ctx, cudaEventRecord(ev1, st));
+    if (ev1 && !one_kernel) G16_CUDA(ctx, cudaEventRecord(ev1, st));
     if (getenv("G16_DEBUG_MSM")) {  // diagnostics only: synchronises
         uint32_t ntasks = 0, totals[kBaMaxLevels + 1] = {};
         cudaStreamSynchronize(st);

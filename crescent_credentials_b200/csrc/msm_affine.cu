@@ -354,7 +354,7 @@ int ba_build_levels(g16_ctx* ctx, MsmScratch* dg, unsigned nseg, uint32_t nb, in
 
 template <class F>
 static int ba_run_levels_t(g16_ctx* ctx, const MsmBases* mb, MsmScratch* sc, const MsmScratch* dg, size_t items, size_t nbuckets,
-                           int levels, const void** out_pts, cudaStream_t st) {
+                           int levels, const void** out_pts, cudaStream_t st, cudaEvent_t add0_ev0, cudaEvent_t add0_ev1) {
     const Affine<F>* src = (const Affine<F>*)mb->pts;
     for (int k = 0; k < levels; k++) {
         size_t cap = ba_level_cap(items, nbuckets, k + 1);
@@ -372,8 +372,10 @@ static int ba_run_levels_t(g16_ctx* ctx, const MsmBases* mb, MsmScratch* sc, con
         if (k == 0) {
             G16_LAUNCH(ctx, (k_ba_products<F, true>), grid, 128, 0, st, src, dg->s_vals, in_start, in_cnt, out_off, nbuckets, tb_first, pre, T);
             G16_TRY(ba_invert(ctx, out_off, nbuckets, threads, T, Q, st));
+            if (add0_ev0) G16_CUDA(ctx, cudaEventRecord(add0_ev0, st));
             G16_LAUNCH(ctx, (k_ba_add<F, true>), grid, 128, 0, st, src, dg->s_vals, in_start, in_cnt, out_off, nbuckets, tb_last,
                        (const Fq*)pre, (const Fq*)Q, dst);
+            if (add0_ev1) G16_CUDA(ctx, cudaEventRecord(add0_ev1, st));
         } else {
             G16_LAUNCH(ctx, (k_ba_products<F, false>), grid, 128, 0, st, src, (const uint32_t*)nullptr, in_start, in_cnt, out_off, nbuckets,
                        tb_first, pre, T);
@@ -388,9 +390,9 @@ static int ba_run_levels_t(g16_ctx* ctx, const MsmBases* mb, MsmScratch* sc, con
 }
 
 int ba_run_levels(g16_ctx* ctx, const MsmBases* mb, MsmScratch* sc, const MsmScratch* dg, size_t items, size_t nbuckets,
-                  int levels, const void** out_pts, cudaStream_t st) {
-    if (mb->group == 1) return ba_run_levels_t<Fq>(ctx, mb, sc, dg, items, nbuckets, levels, out_pts, st);
-    return ba_run_levels_t<Fq2>(ctx, mb, sc, dg, items, nbuckets, levels, out_pts, st);
+                  int levels, const void** out_pts, cudaStream_t st, cudaEvent_t add0_ev0, cudaEvent_t add0_ev1) {
+    if (mb->group == 1) return ba_run_levels_t<Fq>(ctx, mb, sc, dg, items, nbuckets, levels, out_pts, st, add0_ev0, add0_ev1);
+    return ba_run_levels_t<Fq2>(ctx, mb, sc, dg, items, nbuckets, levels, out_pts, st, add0_ev0, add0_ev1);
 }
 
 }  // namespace g16

@@ -64,8 +64,8 @@ void ba_free(MsmScratch* sc);
 // level tables of a digit set: per-bucket point counts and offsets after every pairwise level (point independent)
 int ba_build_levels(g16_ctx* ctx, MsmScratch* dg, unsigned nseg, uint32_t nb, int levels, cudaStream_t st);
 // runs `levels` batched-affine levels over the sorted references of `dg`; leaves the surviving points (affine, sign applied)
-// in *out_pts, laid out by dg's level-`levels` offsets
+// in *out_pts, laid out by dg's level-`levels` offsets.  add0_ev0/1 (optional) bracket the first level's k_ba_add launch.
 int ba_run_levels(g16_ctx* ctx, const MsmBases* mb, MsmScratch* sc, const MsmScratch* dg, size_t items, size_t nbuckets,
-                  int levels, const void** out_pts, cudaStream_t st);
+                  int levels, const void** out_pts, cudaStream_t st, cudaEvent_t add0_ev0 = nullptr, cudaEvent_t add0_ev1 = nullptr);
 
 }  // namespace g16

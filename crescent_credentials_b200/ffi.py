@@ -28,7 +28,7 @@ EXPORTS = [
     "g16_msm_run_dev", "g16_ntt", "g16_ntt_dev", "g16_field_op", "g16_fixed_base_g1", "g16_fixed_base_g2",
     "g16_fixed_base_g1_dev", "g16_fixed_base_g2_dev", "g16_r1cs_eval", "g16_dev_alloc", "g16_dev_free",
     "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count", "g16_set_option",
-    "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare",
+    "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare", "g16_get_msm_stats",
 ]
 
 _u64p = C.POINTER(C.c_uint64)
@@ -116,6 +116,7 @@ def load_library() -> C.CDLL:
     lib.g16_prove_shard_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.g16_copy_partial_dev.argtypes = [C.c_void_p, C.c_void_p]
     lib.g16_prove_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.g16_get_msm_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.g16_prove_combine_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
     lib.g16_witness_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.g16_domain_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
@@ -347,6 +348,15 @@ class Context:
         r = np.ascontiguousarray(r, dtype=np.uint64)
         s = np.ascontiguousarray(s, dtype=np.uint64)
         self.check(self.lib.g16_prove_shard_dev(self.h, _ptr(r), _ptr(s), reduction))
+
+    def msm_stats(self, which: int) -> dict:
+        """Geometry of the last run of one of the proof's MSMs (0 = h, 1 = l, 2 = a, 3 = b_g1, 4 = b_g2)."""
+        out = np.zeros(16, dtype=np.uint64)
+        self.check(self.lib.g16_get_msm_stats(self.h, which, _ptr(out), 16))
+        levels = int(out[3])
+        return {"points": int(out[0]), "window_bits": int(out[1]), "windows": int(out[2]), "levels": levels,
+                "buckets": int(out[4]), "shared_digits": bool(out[5]), "tail_tasks": int(out[6]),
+                "level_points": [int(v) for v in out[8:8 + levels]]}
 
     def prove_prepare(self, r, s):
         r = np.ascontiguousarray(r, dtype=np.uint64)

@@ -116,7 +116,7 @@ typedef struct g16_timings {
     float msm_h_ms, msm_l_ms, msm_a_ms, msm_b_g1_ms, msm_b_g2_ms;
     float assemble_ms;    /* scalar muls, "Finish C", normalisation */
     float total_ms;       /* "Groth16::Prover" */
-    /* with option "kernel_events": duration of the bucket-accumulation kernel of each MSM (h, l, a, b_g1, b_g2) */
+    /* with option "kernel_events": duration of the bucket accumulation of each MSM (h, l, a, b_g1, b_g2) */
     float acc_ms[5];
     float assemble_kernel_ms; /* k_assemble_post alone (assemble_ms also covers the proof read-back) */
     float _reserved[2];
@@ -167,8 +167,11 @@ int g16_witness_map(g16_ctx* ctx, const uint64_t* z, int reduction, uint64_t* h_
 int g16_domain_size(g16_ctx* ctx, size_t* n_out);
 int g16_get_timings(g16_ctx* ctx, g16_timings* out);
 /* Options: "serialize" = 1 runs every stage on the main stream (no overlap; for per-kernel timing),
- * "kernel_events" = 1 brackets the bucket-accumulation kernels with CUDA events (fills g16_timings.acc_ms),
- * "window_bits" = c forces the Pippenger window of bases loaded afterwards (0 = automatic). */
+ * "kernel_events" = 1 brackets the bucket accumulation of every MSM (batched-affine levels + XYZZ tail) with CUDA events
+ *   (fills g16_timings.acc_ms); = 2 brackets only the first level's k_ba_add launch (the dominant kernel),
+ * "window_bits" = c forces the Pippenger window of bases loaded afterwards (0 = automatic),
+ * "ba_levels" = L runs L pairwise batched-affine levels before the XYZZ tail for bases loaded afterwards (-1 = default 5,
+ *   0 = XYZZ only), "share_digits" = 0 disables the reuse of one digit stage by a/l and b_g1/b_g2. */
 int g16_set_option(g16_ctx* ctx, const char* key, int value);
 
 /* ---- building blocks (parity hooks and the synthetic sweep) ------------------------------------------------------- */
@@ -214,6 +217,11 @@ int g16_sync(g16_ctx* ctx);
  * (2) Fr Montgomery multiplications, (3) Fq Montgomery multiplications -- the measured denominators of the integer
  * roofline (MEASURED_PEAKS.json carries none). */
 int g16_bench_int_pipe(g16_ctx* ctx, int which, double* gops_out);
+/* Geometry of the last run of one of the proof's MSMs (which: 0 = h, 1 = l, 2 = a, 3 = b_g1, 4 = b_g2), for the bench's
+ * per-launch work figures: out[0] points, [1] window bits c, [2] windows, [3] batched-affine levels, [4] buckets,
+ * [5] 1 if the digit stage is shared with another MSM, [6] XYZZ tail tasks, [8..8+levels) points left after each level
+ * (= additions-or-copies the level's kernels process).  capacity >= 16.  Synchronises. */
+int g16_get_msm_stats(g16_ctx* ctx, int which, uint64_t* out, int capacity);
 /* Number of kernels this library has launched on this context since creation (for the bench's gpu_launches claim). */
 uint64_t g16_launch_count(const g16_ctx* ctx);
 

@@ -34,7 +34,8 @@ ctx.load_r1cs(inst.nc, inst.ni, inst.m, inst.matrices.row_ptr, inst.matrices.col
 ctx.set_option("ba_levels", args.ba_levels)
 ctx.set_option("share_digits", args.share_digits)
 ctx.load_pk(pk.arrays, pk.encoding, 0, 1, bool(args.precompute))
-r_m, s_m = g.fr_to_mont([12345])[0], g.fr_to_mont([67890])[0]
+r_m = g.fr_to_mont([0x1111222233334444555566667777888899990000AAAABBBBCCCCDDDD % g.R_MOD])[0]
+s_m = g.fr_to_mont([0x0F0E0D0C0B0A09080706050403020100FFEEDDCCBBAA9988 % g.R_MOD])[0]  # same (r, s) as bench.py
 ctx.upload_witness(inst.z_mont)
 ctx.set_option("serialize", args.serialize)
 ctx.set_option("kernel_events", 1)
