@@ -170,6 +170,11 @@ def main():
     ap.add_argument("--inflight", type=int, default=2,
                     help="extra timed region with this many proofs in flight on one GPU (separate contexts, one host thread "
                          "each); reported as `pipelined`, never as `value`.  0/1 disables it")
+    ap.add_argument("--plan", choices=["staggered", "uniform"], default="staggered",
+                    help="N > 1: staggered = only rank 0 runs the witness map, the other ranks take a larger share of the wire "
+                         "MSMs and receive their h chunk through one NCCL scatter; uniform = every rank runs the witness map")
+    ap.add_argument("--rank0-share", type=float, default=None,
+                    help="staggered plan: rank 0's share of the wire MSMs (default: the balance point of sharded.rank0_wire_share)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     args = ap.parse_args()
@@ -203,7 +208,17 @@ def main():
     ctx.load_r1cs(inst.nc, inst.ni, inst.m, inst.matrices.row_ptr, inst.matrices.col, inst.matrices.val, inst.matrices.encoding)
     ctx.set_option("ba_levels", args.ba_levels)
     ctx.set_option("share_digits", args.share_digits)
-    ctx.load_pk(pk.arrays, pk.encoding, rank, world, bool(args.precompute))
+    from crescent_credentials_b200 import sharded
+    h_len = int(np.asarray(pk.arrays["h_query"]).reshape(-1, 8).shape[0])
+    m1 = int(np.asarray(pk.arrays["a_query"]).reshape(-1, 8).shape[0]) - 1
+    plan = (sharded.staggered_plan(h_len, m1, world, args.rank0_share) if args.plan == "staggered"
+            else sharded.uniform_plan(h_len, m1, world))
+    ctx.load_pk(pk.arrays, pk.encoding, rank, world, bool(args.precompute), h_range=plan.h_ranges[rank], z_range=plan.z_ranges[rank])
+    h_all = h_mine = None
+    if world > 1 and plan.staggered:
+        if rank == plan.wm_rank:
+            h_all = torch.zeros((max(inst.n, world * plan.h_chunk), 4), dtype=torch.int64, device="cuda")
+        h_mine = torch.zeros((plan.h_chunk, 4), dtype=torch.int64, device="cuda")
 
     # pinned host witness for the end-to-end path
     z_pin = torch.from_numpy(inst.z_mont.view(np.int64)).pin_memory()
@@ -218,7 +233,18 @@ def main():
             return ctx.prove_resident(r_m, s_m)
         if rank == 0:
             ctx.prove_prepare(r_m, s_m)
-        ctx.prove_shard_dev(r_m, s_m)
+        if plan.staggered:
+            owner = rank == plan.wm_rank
+            ctx.prove_shard_begin_dev(r_m, s_m, run_witness_map=owner)
+            if owner:
+                ctx.copy_h_dev(h_all.data_ptr(), h_all.shape[0])
+            sharded.scatter_h(h_all, h_mine, plan, rank)   # the one exchange step: n*32/G bytes to every peer
+            if owner:
+                ctx.prove_shard_finish_dev()
+            else:
+                ctx.prove_shard_finish_dev(h_mine.data_ptr(), plan.h_ranges[rank][0], plan.h_chunk)
+        else:
+            ctx.prove_shard_dev(r_m, s_m)
         ctx.copy_partial_dev(my_part.data_ptr())
         dist.all_gather_into_tensor(gather_buf.view(-1), my_part)
         if rank == 0:
@@ -325,10 +351,18 @@ def main():
         finally:
             for c2 in extra:
                 c2.close()
+    rank_stage = None
     if world > 1:
         t = torch.tensor([ms_res, ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_res, ms_e2e = float(t[0]), float(t[1])
+        # per-rank device timings of the last step (diagnostic: where each rank's critical path went)
+        tm = ctx.timings()
+        keys = ["witness_map_ms", "h_wait_ms", "h_start_ms", "msm_h_ms", "msm_l_ms", "msm_a_ms", "msm_b_g1_ms", "msm_b_g2_ms", "total_ms"]
+        mine_t = torch.tensor([tm[k] for k in keys], device="cuda", dtype=torch.float64)
+        all_t = torch.zeros((world, len(keys)), device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(all_t.view(-1), mine_t)
+        rank_stage = {k: [round(float(all_t[r, i]), 3) for r in range(world)] for i, k in enumerate(keys)}
 
     out = None
     if rank == 0:
@@ -401,13 +435,15 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{args.workload} ({args.witness} witness)", "constraints": inst.nc, "wires": inst.m,
                        "domain": inst.n, "nnz": nnz, "parallelism": f"msm-shard{world}" if world > 1 else "single",
+                       "plan": ({"kind": args.plan, "witness_map_rank": plan.wm_rank, "rank0_wire_share": round(plan.z_ranges[0][1] / max(m1, 1), 4),
+                                 "h_scatter_bytes_per_peer": plan.h_chunk * 32 if plan.staggered else 0} if world > 1 else None),
                        "l2": "inputs>L2 (pk+scratch ~GBs)", "precompute": args.precompute,
                        "window_bits": args.window_bits or "auto (19 at this size)", "ba_levels": args.ba_levels},
             "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(inst.z_mont.nbytes), "d2h_bytes_per_step": 256},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "roofline_int": roof_int,
             "accumulation_stage": acc_stage,
-            "pipelined": pipelined, "cpu_baseline": cpu, "stage_ms": stage, "proof_verified_in_exponent": verified,
+            "pipelined": pipelined, "cpu_baseline": cpu, "stage_ms": stage, "rank_stage_ms": rank_stage, "proof_verified_in_exponent": verified,
             "prove_ms": ms_res / args.steps,
         }
         print(json.dumps(out), flush=True)

@@ -487,9 +487,10 @@ static int load_query(g16_ctx* ctx, int qi, int group, const uint64_t* pts, size
     return rc;
 }
 
-int g16_ctx_load_pk(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int shard_count, int precompute) {
-    if (!ctx || !pk) return G16_ERR_BAD_ARG;
-    Guard g(ctx);
+// h_range / z_range (optional): this rank's point range of h_query and of the a / b_g1 / b_g2 queries (index space of
+// query[1..]); NULL = the uniform split [rank*N/G, (rank+1)*N/G).
+static int load_pk_ranges(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int shard_count, const uint64_t* h_range,
+                          const uint64_t* z_range, int precompute) {
     if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count)
         return set_err(ctx, G16_ERR_BAD_ARG, "shard %d of %d is not a valid rank", shard_rank, shard_count);
     if (!pk->alpha_g1 || !pk->beta_g1 || !pk->delta_g1 || !pk->beta_g2 || !pk->delta_g2)
@@ -516,10 +517,18 @@ int g16_ctx_load_pk(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int sha
         *hi = total * (size_t)(shard_rank + 1) / (size_t)shard_count;
     };
     size_t lo, hi;
-    range(pk->h_len, &lo, &hi);
-    G16_TRY(load_query(ctx, Q_H, 1, pk->h_query, pk->h_len, lo, hi, enc, precompute));
     size_t m1 = pk->a_len - 1;  // MSM over query[1..] (prover.rs:266)
-    range(m1, &lo, &hi);
+    if (h_range && (h_range[0] > h_range[1] || h_range[1] > pk->h_len))
+        return set_err(ctx, G16_ERR_BAD_ARG, "pk: h range [%llu, %llu) outside h_query (%zu points)", (unsigned long long)h_range[0],
+                       (unsigned long long)h_range[1], pk->h_len);
+    if (z_range && (z_range[0] > z_range[1] || z_range[1] > m1))
+        return set_err(ctx, G16_ERR_BAD_ARG, "pk: wire range [%llu, %llu) outside a_query[1..] (%zu points)", (unsigned long long)z_range[0],
+                       (unsigned long long)z_range[1], m1);
+    if (h_range) lo = (size_t)h_range[0], hi = (size_t)h_range[1];
+    else range(pk->h_len, &lo, &hi);
+    G16_TRY(load_query(ctx, Q_H, 1, pk->h_query, pk->h_len, lo, hi, enc, precompute));
+    if (z_range) lo = (size_t)z_range[0], hi = (size_t)z_range[1];
+    else range(m1, &lo, &hi);
     G16_TRY(load_query(ctx, Q_A, 1, pk->a_query + 8, m1, lo, hi, enc, precompute));
     G16_TRY(load_query(ctx, Q_B1, 1, pk->b_g1_query + 8, m1, lo, hi, enc, precompute));
     G16_TRY(load_query(ctx, Q_B2, 2, pk->b_g2_query + 16, m1, lo, hi, enc, precompute));
@@ -538,6 +547,9 @@ int g16_ctx_load_pk(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int sha
     if (aligned) {
         l_lo = (lo > shift ? lo : shift) - shift;
         l_hi = (hi > shift ? hi : shift) - shift;
+    } else if (z_range) {  // l_query longer than a_query[1..] never happens for a Groth16 key; keep the ranges a partition anyway
+        l_lo = m1 ? pk->l_len * lo / m1 : 0;
+        l_hi = m1 ? pk->l_len * hi / m1 : 0;
     } else {
         range(pk->l_len, &l_lo, &l_hi);
     }
@@ -567,6 +579,18 @@ int g16_ctx_load_pk(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int sha
     return G16_OK;
 }
 
+int g16_ctx_load_pk(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int shard_count, int precompute) {
+    if (!ctx || !pk) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    return load_pk_ranges(ctx, pk, shard_rank, shard_count, nullptr, nullptr, precompute);
+}
+int g16_ctx_load_pk_ranges(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int shard_count, const uint64_t h_range[2],
+                           const uint64_t z_range[2], int precompute) {
+    if (!ctx || !pk || !h_range || !z_range) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "load_pk_ranges: null argument") : G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    return load_pk_ranges(ctx, pk, shard_rank, shard_count, h_range, z_range, precompute);
+}
+
 // ---- prove ------------------------------------------------------------------------------------------------------------------------
 static int check_ready(g16_ctx* ctx) {
     if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "prove: no R1CS loaded");
@@ -588,7 +612,10 @@ struct PartialLayout {
 
 // Runs witness map + the five (sharded) MSMs; leaves this rank's partial sums in ctx->d_partial.  Witness must be on the
 // device (ordered on main).  Work fans out from `main` to the side streams and joins back.
-static int prove_shard_streams(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int reduction) {
+// Split in two so that a rank which does not run the witness map itself can receive h between the halves:
+//   shard_begin  forks the z-only MSMs onto the side streams and (run_wm) runs the witness map on main;
+//   shard_finish runs the h MSM on main over h_src (NULL = the witness map's own output) and joins the side streams.
+static int shard_begin(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int reduction, bool run_wm) {
     cudaStream_t main = ctx->main;
     PartialLayout* part = (PartialLayout*)ctx->d_partial;
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
@@ -620,7 +647,9 @@ static int prove_shard_streams(g16_ctx* ctx, const uint64_t* r, const uint64_t* 
         chains[nchains][0] = {Q_B2, -1};
         chain_len[nchains++] = 1;
     }
-    bool scaled[2] = {false, false};
+    bool* scaled = ctx->sh_scaled;
+    scaled[0] = scaled[1] = false;
+    ctx->sh_nchains = nchains;
     for (int k = 0; k < nchains; k++) {
         cudaStream_t st = ctx->opt_serialize ? main : ctx->side[k];
         if (!ctx->opt_serialize) G16_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
@@ -670,14 +699,23 @@ static int prove_shard_streams(g16_ctx* ctx, const uint64_t* r, const uint64_t* 
         }
         if (!ctx->opt_serialize) G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], st));
     }
-    // main: witness map, then the h MSM over h[lo..hi)  (prover.rs:63-66; the zip drops h[n-1], generator.rs:178)
+    // main: witness map (r1cs_to_qap.rs:150-213)
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[0], main));
-    G16_TRY(witness_map_dev(ctx, reduction, main));
+    if (run_wm) G16_TRY(witness_map_dev(ctx, reduction, main));
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[1], main));
+    return G16_OK;
+}
+
+static int shard_finish(g16_ctx* ctx, const Fr* h_src) {
+    cudaStream_t main = ctx->main;
+    PartialLayout* part = (PartialLayout*)ctx->d_partial;
+    const int nchains = ctx->sh_nchains;
+    const bool* scaled = ctx->sh_scaled;
+    // the h MSM over h[lo..hi)  (prover.rs:63-66; the zip drops h[n-1], generator.rs:178)
     {
         size_t cnt = ctx->sh_hi[Q_H] - ctx->sh_lo[Q_H];
         G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * Q_H], main));
-        G16_TRY(msm_run(ctx, &ctx->q[Q_H], &ctx->scratch[Q_H], ctx->d_a + ctx->sh_lo[Q_H], cnt, main,
+        G16_TRY(msm_run(ctx, &ctx->q[Q_H], &ctx->scratch[Q_H], (h_src ? h_src : ctx->d_a) + ctx->sh_lo[Q_H], cnt, main,
                         ctx->opt_kernel_events ? ctx->ev_acc[0] : nullptr, ctx->opt_kernel_events ? ctx->ev_acc[1] : nullptr));
         if (cnt && ctx->scratch[Q_H].result)
             G16_CUDA(ctx, cudaMemcpyAsync(&part->h, ctx->scratch[Q_H].result, sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, main));
@@ -691,6 +729,11 @@ static int prove_shard_streams(g16_ctx* ctx, const uint64_t* r, const uint64_t* 
             if (scaled[k]) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[5 + k], 0));
     }
     return G16_OK;
+}
+
+static int prove_shard_streams(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int reduction) {
+    G16_TRY(shard_begin(ctx, r, s, reduction, true));
+    return shard_finish(ctx, nullptr);
 }
 
 static void collect_timings(g16_ctx* ctx, bool with_asm) {
@@ -709,6 +752,8 @@ static void collect_timings(g16_ctx* ctx, bool with_asm) {
     ctx->tm.msm_b_g1_ms = el(8, 9);
     ctx->tm.msm_b_g2_ms = el(10, 11);
     ctx->tm.h2d_ms = el(14, 0);
+    ctx->tm.h_wait_ms = el(1, 2);
+    ctx->tm.h_start_ms = el(14, 2);
     for (int k = 0; k < 5; k++) {
         float ms = -1;
         if (ctx->opt_kernel_events && cudaEventElapsedTime(&ms, ctx->ev_acc[2 * k], ctx->ev_acc[2 * k + 1]) != cudaSuccess) {
@@ -778,6 +823,44 @@ int g16_prove_shard_dev(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], 
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[14], ctx->main));
     G16_TRY(prove_shard_streams(ctx, r, s, reduction));
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[12], ctx->main));
+    ctx->tm_stale = true;
+    return G16_OK;
+}
+
+int g16_prove_shard_begin_dev(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], int reduction, int run_witness_map) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    if (!r || !s) return set_err(ctx, G16_ERR_BAD_ARG, "prove_shard_begin: null r/s");
+    Guard g(ctx);
+    G16_TRY(check_ready(ctx));
+    if (!ctx->witness_resident) return set_err(ctx, G16_ERR_BAD_ARG, "prove_shard_begin_dev: no witness uploaded");
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[14], ctx->main));
+    G16_TRY(shard_begin(ctx, r, s, reduction, run_witness_map != 0));
+    ctx->shard_open = true;
+    return G16_OK;
+}
+
+int g16_prove_shard_finish_dev(g16_ctx* ctx, const void* h_dev, size_t h_first, size_t h_count) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!ctx->shard_open) return set_err(ctx, G16_ERR_BAD_ARG, "prove_shard_finish_dev without prove_shard_begin_dev");
+    ctx->shard_open = false;
+    if (h_dev && (h_first > ctx->sh_lo[Q_H] || h_first + h_count < ctx->sh_hi[Q_H]))
+        return set_err(ctx, G16_ERR_BAD_ARG, "prove_shard_finish: h[%zu, %zu) does not cover this rank's range [%zu, %zu)", h_first,
+                       h_first + h_count, ctx->sh_lo[Q_H], ctx->sh_hi[Q_H]);
+    // shard_finish indexes its source by the absolute coefficient index
+    G16_TRY(shard_finish(ctx, h_dev ? (const Fr*)h_dev - h_first : nullptr));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[12], ctx->main));
+    ctx->tm_stale = true;
+    return G16_OK;
+}
+
+int g16_copy_h_dev(g16_ctx* ctx, void* dst_dev, size_t capacity_elems) {
+    if (!ctx || !dst_dev) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "copy_h: no R1CS loaded");
+    size_t n = (size_t)1 << ctx->log_n;
+    if (capacity_elems < n) return set_err(ctx, G16_ERR_BAD_ARG, "copy_h: buffer holds %zu < %zu elements", capacity_elems, n);
+    G16_CUDA(ctx, cudaMemcpyAsync(dst_dev, ctx->d_a, n * 32, cudaMemcpyDeviceToDevice, ctx->main));
     return G16_OK;
 }
 
@@ -916,6 +999,12 @@ int g16_get_msm_stats(g16_ctx* ctx, int which, uint64_t* out, int capacity) {
 
 int g16_get_timings(g16_ctx* ctx, g16_timings* out) {
     if (!ctx || !out) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (ctx->tm_stale) {  // the *_dev shard entry points do not synchronise: read their events now
+        G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+        collect_timings(ctx, false);
+        ctx->tm_stale = false;
+    }
     *out = ctx->tm;
     return G16_OK;
 }

@@ -24,7 +24,6 @@ namespace g16 {
 struct dfma {
     static constexpr uint64_t M52 = (1ull << 52) - 1;
     static constexpr uint64_t M48 = (1ull << 48) - 1;
-    static constexpr uint64_t M56 = (1ull << 56) - 1;
     static constexpr uint64_t EXP52 = 0x4330000000000000ull;   // bits of 2^52
     static constexpr uint64_t EXP104 = 0x4670000000000000ull;  // bits of 2^104
 
@@ -147,25 +146,30 @@ G16_HD Fp<PR> mul_dfma(const Fp<PR>& a, const Fp<PR>& b) {
         }
         if (i < 4) col[i + 1] += col[i] >> 52;  // low 52 bits are zero now
     }
-    // value = (col[4] >> 48) + col[5] * 2^4 + col[6] * 2^56 + ... : renormalise to 56-bit digits
-    uint64_t d[5];
-    uint64_t c = col[4] >> 48;
+    // value = (col[4] >> 48) + 2^4 * sum_k col[5 + k] * 2^(52 k): renormalise the columns to 52-bit digits, then repack
+    uint64_t u = col[4] >> 48;  // < 2^10
+    uint64_t e[5];
+    uint64_t c = u >> 4;
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-        uint64_t w = (col[5 + k] << 4) + c;  // col < 2^58
-        d[k] = w & dfma::M56;
-        c = w >> 56;
+    for (int k = 0; k < 4; k++) {
+        uint64_t w = col[5 + k] + c;
+        e[k] = w & dfma::M52;
+        c = w >> 52;
     }
-    d[4] |= c << 56;  // result < 2p < 2^255: everything above bit 224 fits the last word
+    e[4] = col[9] + c;  // result < 2p < 2^255: the top digit needs no mask
+    uint64_t w0 = (u & 15) | (e[0] << 4) | (e[1] << 56);
+    uint64_t w1 = (e[1] >> 8) | (e[2] << 44);
+    uint64_t w2 = (e[2] >> 20) | (e[3] << 32);
+    uint64_t w3 = (e[3] >> 32) | (e[4] << 20);
     Fp<PR> r;
-    r.v[0] = (uint32_t)d[0];
-    r.v[1] = (uint32_t)(d[0] >> 32) | (uint32_t)(d[1] << 24);
-    r.v[2] = (uint32_t)(d[1] >> 8);
-    r.v[3] = (uint32_t)(d[1] >> 40) | (uint32_t)(d[2] << 16);
-    r.v[4] = (uint32_t)(d[2] >> 16);
-    r.v[5] = (uint32_t)(d[2] >> 48) | (uint32_t)(d[3] << 8);
-    r.v[6] = (uint32_t)(d[3] >> 24);
-    r.v[7] = (uint32_t)d[4];
+    r.v[0] = (uint32_t)w0;
+    r.v[1] = (uint32_t)(w0 >> 32);
+    r.v[2] = (uint32_t)w1;
+    r.v[3] = (uint32_t)(w1 >> 32);
+    r.v[4] = (uint32_t)w2;
+    r.v[5] = (uint32_t)(w2 >> 32);
+    r.v[6] = (uint32_t)w3;
+    r.v[7] = (uint32_t)(w3 >> 32);
     Fp<PR>::reduce_once(r.v, 0);
     return r;
 }

@@ -130,6 +130,10 @@ struct g16_ctx {
     int opt_ba_levels = -1;  // batched-affine levels (-1 = default)
     int opt_share_digits = 1;
     bool share_al = false, share_b = false;  // l reuses a's digit stage / b_g2 reuses b_g1's
+    int sh_nchains = 0;                       // state handed from shard_begin to shard_finish (api.cu)
+    bool sh_scaled[2] = {false, false};
+    bool shard_open = false;
+    bool tm_stale = false;  // events of a *_dev shard run not yet read into tm
     cudaEvent_t ev_acc[10] = {};
     bool pre_pending = false;  // k_assemble_pre already in flight for (pre_r, pre_s)
     uint64_t pre_r[4] = {}, pre_s[4] = {};

@@ -28,7 +28,8 @@ EXPORTS = [
     "g16_msm_run_dev", "g16_ntt", "g16_ntt_dev", "g16_field_op", "g16_fixed_base_g1", "g16_fixed_base_g2",
     "g16_fixed_base_g1_dev", "g16_fixed_base_g2_dev", "g16_r1cs_eval", "g16_dev_alloc", "g16_dev_free",
     "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count", "g16_set_option",
-    "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare", "g16_get_msm_stats",
+    "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare", "g16_get_msm_stats", "g16_ctx_load_pk_ranges",
+    "g16_prove_shard_begin_dev", "g16_prove_shard_finish_dev", "g16_copy_h_dev",
 ]
 
 _u64p = C.POINTER(C.c_uint64)
@@ -66,12 +67,14 @@ class Partial(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "witness_map_ms", "msm_h_ms", "msm_l_ms", "msm_a_ms",
                                          "msm_b_g1_ms", "msm_b_g2_ms", "assemble_ms", "total_ms")] + [
-        ("acc_ms", C.c_float * 5), ("assemble_kernel_ms", C.c_float), ("_reserved", C.c_float * 2)]
+        ("acc_ms", C.c_float * 5), ("assemble_kernel_ms", C.c_float), ("h_wait_ms", C.c_float), ("h_start_ms", C.c_float)]
 
     def as_dict(self):
         d = {n: float(getattr(self, n)) for n, _ in self._fields_[:9]}
         d["acc_ms"] = dict(zip(("h", "l", "a", "b_g1", "b_g2"), (float(x) for x in self.acc_ms)))
         d["assemble_kernel_ms"] = float(self.assemble_kernel_ms)
+        d["h_wait_ms"] = float(self.h_wait_ms)
+        d["h_start_ms"] = float(self.h_start_ms)
         return d
 
 
@@ -106,6 +109,10 @@ def load_library() -> C.CDLL:
     lib.g16_ctx_destroy.argtypes = [C.c_void_p]
     lib.g16_ctx_destroy.restype = None
     lib.g16_ctx_load_pk.argtypes = [C.c_void_p, C.POINTER(PkView), C.c_int, C.c_int, C.c_int]
+    lib.g16_ctx_load_pk_ranges.argtypes = [C.c_void_p, C.POINTER(PkView), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.g16_prove_shard_begin_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.g16_prove_shard_finish_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    lib.g16_copy_h_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.g16_ctx_load_r1cs.argtypes = [C.c_void_p, C.POINTER(R1csView)]
     lib.g16_prove.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ProofOut)]
     lib.g16_upload_witness.argtypes = [C.c_void_p, C.c_void_p]
@@ -276,9 +283,11 @@ class Context:
             v.val[k] = C.cast(vv.ctypes.data, _u64p)
         self.check(self.lib.g16_ctx_load_r1cs(self.h, C.byref(v)))
 
-    def load_pk(self, arrays: dict, encoding=ENC_MONTGOMERY, shard_rank=0, shard_count=1, precompute=False):
+    def load_pk(self, arrays: dict, encoding=ENC_MONTGOMERY, shard_rank=0, shard_count=1, precompute=False,
+                h_range=None, z_range=None):
         """arrays: a_query, b_g1_query, b_g2_query, h_query, l_query (n x 8 / n x 16 uint64) and the single points
-        alpha_g1, beta_g1, delta_g1 (8), beta_g2, delta_g2 (16)."""
+        alpha_g1, beta_g1, delta_g1 (8), beta_g2, delta_g2 (16).  h_range / z_range: explicit [lo, hi) point ranges of
+        this rank (g16_ctx_load_pk_ranges) instead of the uniform split."""
         v = PkView()
         keep = {}
         for name in ("a_query", "b_g1_query", "b_g2_query", "h_query", "l_query"):
@@ -292,7 +301,12 @@ class Context:
             keep[name] = a
             setattr(v, name, C.cast(a.ctypes.data, _u64p))
         v.encoding = encoding
-        self.check(self.lib.g16_ctx_load_pk(self.h, C.byref(v), shard_rank, shard_count, int(precompute)))
+        if h_range is None and z_range is None:
+            self.check(self.lib.g16_ctx_load_pk(self.h, C.byref(v), shard_rank, shard_count, int(precompute)))
+        else:
+            hr = np.array(h_range, dtype=np.uint64)
+            zr = np.array(z_range, dtype=np.uint64)
+            self.check(self.lib.g16_ctx_load_pk_ranges(self.h, C.byref(v), shard_rank, shard_count, _ptr(hr), _ptr(zr), int(precompute)))
 
     def domain_size(self) -> int:
         n = C.c_size_t(0)
@@ -348,6 +362,18 @@ class Context:
         r = np.ascontiguousarray(r, dtype=np.uint64)
         s = np.ascontiguousarray(s, dtype=np.uint64)
         self.check(self.lib.g16_prove_shard_dev(self.h, _ptr(r), _ptr(s), reduction))
+
+    def prove_shard_begin_dev(self, r, s, reduction=REDUCTION_LIBSNARK, run_witness_map=True):
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        self.check(self.lib.g16_prove_shard_begin_dev(self.h, _ptr(r), _ptr(s), reduction, int(run_witness_map)))
+
+    def prove_shard_finish_dev(self, h_dev: int = 0, h_first: int = 0, h_count: int = 0):
+        """h_dev: device pointer holding h[h_first, h_first + h_count) (0 = this context's own witness-map output)."""
+        self.check(self.lib.g16_prove_shard_finish_dev(self.h, C.c_void_p(h_dev) if h_dev else None, h_first, h_count))
+
+    def copy_h_dev(self, dst_dev: int, capacity_elems: int):
+        self.check(self.lib.g16_copy_h_dev(self.h, C.c_void_p(dst_dev), capacity_elems))
 
     def msm_stats(self, which: int) -> dict:
         """Geometry of the last run of one of the proof's MSMs (0 = h, 1 = l, 2 = a, 3 = b_g1, 4 = b_g2)."""

@@ -1,21 +1,72 @@
-"""MSM-sharded proving over the GPUs of one box: one process per GPU, every rank holds the contiguous point
-range [rank*N/G, (rank+1)*N/G) of each of the five queries, runs the witness map and its five partial MSMs, and the
-G partial results (768 bytes per rank: 4 x G1 XYZZ + 1 x G2 XYZZ) are gathered with ONE small collective
-(torch.distributed: NCCL over NVLink on the GPUs, gloo in the CPU tests).  Rank 0 adds the partials and assembles.
-There is no other data-path collective: the witness goes host -> each GPU directly."""
+"""MSM-sharded proving over the GPUs of one box: one process per GPU, every rank holds a contiguous point
+range of each of the five queries and runs its five partial MSMs; the G partial results (896 bytes per rank: 5 x G1 XYZZ
++ 1 x G2 XYZZ) are gathered with ONE small collective (torch.distributed: NCCL over NVLink on the GPUs, gloo in the CPU
+tests) and rank 0 adds the partials and assembles.
+
+Two plans:
+  uniform    every rank takes [rank*N/G, (rank+1)*N/G) of every query and runs the whole witness map itself (no h exchange).
+  staggered  (default for G > 1) the witness map does not shard (north star: "NTT and witness_map stay on one GPU"), so
+             replicating it puts ~4 ms on every rank's critical path.  Instead rank 0 alone runs it while the other ranks
+             spend that time on a LARGER share of the z-only MSMs (a, l, b_g1, b_g2); rank 0 then scatters the h
+             coefficients (n*32/G bytes per peer, one NCCL scatter over NVLink) and every rank finishes with its h-MSM
+             range.  Rank 0's share f0 of the wire MSMs balances  wm + f0*Z  against  (1 - f0)*Z/(G - 1).
+The witness goes host -> each GPU directly in both plans."""
 from __future__ import annotations
 
-from typing import Optional
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
 
 import numpy as np
 
 from . import ffi
 from .groth16 import Proof, ProvingKey, ConstraintMatrices, fr_to_mont, R_MOD
 
+# witness-map time over the time of the four z-only MSMs on one B200 (S-rs256: 4.25 ms vs ~15 ms); only the balance of the
+# staggered plan depends on it, never a result
+WM_OVER_Z = 0.28
+
 
 def shard_range(total: int, rank: int, world: int):
     """Same split as g16_ctx_load_pk: [total*rank/world, total*(rank+1)/world)."""
     return total * rank // world, total * (rank + 1) // world
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    wm_rank: int                       # rank that runs the witness map; -1 = every rank (uniform plan)
+    h_chunk: int                       # staggered: h coefficients per rank in the scatter (equal chunks)
+    h_ranges: List[Tuple[int, int]]    # per rank [lo, hi) of h_query
+    z_ranges: List[Tuple[int, int]]    # per rank [lo, hi) of a_query[1..] / b_g1_query[1..] / b_g2_query[1..]
+
+    @property
+    def staggered(self) -> bool:
+        return self.wm_rank >= 0
+
+
+def uniform_plan(h_len: int, m1: int, world: int) -> ShardPlan:
+    return ShardPlan(world, -1, 0, [shard_range(h_len, r, world) for r in range(world)],
+                     [shard_range(m1, r, world) for r in range(world)])
+
+
+def rank0_wire_share(world: int, wm_over_z: float = WM_OVER_Z) -> float:
+    """f0 with  wm + f0*Z == (1 - f0)*Z/(G - 1)  (clamped at 0: from ~5 ranks on rank 0 takes no wire MSM work at all)."""
+    if world <= 1:
+        return 1.0
+    per_other = 1.0 / (world - 1)
+    return max(0.0, (per_other - wm_over_z) / (1.0 + per_other))
+
+
+def staggered_plan(h_len: int, m1: int, world: int, rank0_share: Optional[float] = None) -> ShardPlan:
+    if world == 1:
+        return uniform_plan(h_len, m1, 1)
+    f0 = rank0_wire_share(world) if rank0_share is None else min(max(float(rank0_share), 0.0), 1.0)
+    cut = int(round(m1 * f0))
+    rest = m1 - cut
+    z = [(0, cut)] + [(cut + rest * (r - 1) // (world - 1), cut + rest * r // (world - 1)) for r in range(1, world)]
+    chunk = -(-h_len // world)
+    h = [(min(r * chunk, h_len), min((r + 1) * chunk, h_len)) for r in range(world)]
+    return ShardPlan(world, 0, chunk, h, z)
 
 
 def gather_partials(mine, world: int):
@@ -27,11 +78,19 @@ def gather_partials(mine, world: int):
     return out
 
 
+def scatter_h(h_all, h_mine, plan: ShardPlan, rank: int):
+    """Rank plan.wm_rank holds h in h_all ((>= world * h_chunk, 4) int64); every rank receives its chunk in h_mine."""
+    import torch.distributed as dist
+    c = plan.h_chunk
+    chunks = [h_all[r * c:(r + 1) * c].view(-1) for r in range(plan.world)] if rank == plan.wm_rank else None
+    dist.scatter(h_mine.view(-1), chunks, src=plan.wm_rank)
+
+
 class ShardedProver:
     """Groth16 prover whose MSMs are sharded over torch.distributed ranks (call collectively on every rank)."""
 
     def __init__(self, pk: ProvingKey, matrices: ConstraintMatrices, device: int, rank: int, world: int, stream: int = 0,
-                 precompute: bool = False):
+                 precompute: bool = False, plan: Optional[ShardPlan] = None):
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
@@ -39,21 +98,51 @@ class ShardedProver:
         m = matrices.num_instance_variables + matrices.num_witness_variables
         self.ctx.load_r1cs(matrices.num_constraints, matrices.num_instance_variables, m, matrices.row_ptr, matrices.col,
                            matrices.val, matrices.encoding)
-        self.ctx.load_pk(pk.arrays, pk.encoding, rank, world, precompute)
-        self.mine = torch.zeros((ffi.PARTIAL_U64,), dtype=torch.int64, device=f"cuda:{device}")
+        h_len = int(np.asarray(pk.arrays["h_query"]).reshape(-1, 8).shape[0])
+        m1 = int(np.asarray(pk.arrays["a_query"]).reshape(-1, 8).shape[0]) - 1
+        self.plan = plan if plan is not None else staggered_plan(h_len, m1, world)
+        assert self.plan.world == world
+        self.ctx.load_pk(pk.arrays, pk.encoding, rank, world, precompute, h_range=self.plan.h_ranges[rank],
+                         z_range=self.plan.z_ranges[rank])
+        dev = f"cuda:{device}"
+        self.mine = torch.zeros((ffi.PARTIAL_U64,), dtype=torch.int64, device=dev)
+        self.h_all = self.h_mine = None
+        if self.plan.staggered:
+            n = self.ctx.domain_size()
+            cap = max(n, world * self.plan.h_chunk)
+            if rank == self.plan.wm_rank:
+                self.h_all = torch.zeros((cap, 4), dtype=torch.int64, device=dev)
+            self.h_mine = torch.zeros((self.plan.h_chunk, 4), dtype=torch.int64, device=dev)
+
+    def prove_resident(self, rr, ss, reduction=ffi.REDUCTION_LIBSNARK):
+        """Witness already uploaded; (rr, ss) Montgomery.  Returns the raw proof on rank 0, None elsewhere."""
+        ctx, plan, rank = self.ctx, self.plan, self.rank
+        if rank == 0:
+            ctx.prove_prepare(rr, ss)   # overlaps r*delta, s*delta, ... with the shard MSMs
+        if plan.staggered:
+            owner = rank == plan.wm_rank
+            ctx.prove_shard_begin_dev(rr, ss, reduction, run_witness_map=owner)
+            if owner:
+                ctx.copy_h_dev(self.h_all.data_ptr(), self.h_all.shape[0])
+            scatter_h(self.h_all, self.h_mine, plan, rank)
+            if owner:
+                ctx.prove_shard_finish_dev()
+            else:
+                ctx.prove_shard_finish_dev(self.h_mine.data_ptr(), plan.h_ranges[rank][0], plan.h_chunk)
+        else:
+            ctx.prove_shard_dev(rr, ss, reduction)
+        ctx.copy_partial_dev(self.mine.data_ptr())
+        allp = gather_partials(self.mine, self.world)
+        if rank != 0:
+            return None
+        return ctx.prove_combine_dev(allp.data_ptr(), self.world, rr, ss)
 
     def prove(self, z_mont, r: int, s: int, reduction=ffi.REDUCTION_LIBSNARK) -> Optional[Proof]:
         """z_mont: (m, 4) uint64 Montgomery witness (same on every rank).  Returns the proof on rank 0, None elsewhere."""
         rr, ss = fr_to_mont([r % R_MOD])[0], fr_to_mont([s % R_MOD])[0]
         self.ctx.upload_witness(z_mont)
-        if self.rank == 0:
-            self.ctx.prove_prepare(rr, ss)   # overlaps r*delta, s*delta, ... with the shard MSMs
-        self.ctx.prove_shard_dev(rr, ss, reduction)
-        self.ctx.copy_partial_dev(self.mine.data_ptr())
-        allp = gather_partials(self.mine, self.world)
-        if self.rank != 0:
-            return None
-        return Proof.from_ffi(self.ctx.prove_combine_dev(allp.data_ptr(), self.world, rr, ss))
+        raw = self.prove_resident(rr, ss, reduction)
+        return None if raw is None else Proof.from_ffi(raw)
 
     def close(self):
         self.ctx.close()

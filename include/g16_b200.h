@@ -119,7 +119,8 @@ typedef struct g16_timings {
     /* with option "kernel_events": duration of the bucket accumulation of each MSM (h, l, a, b_g1, b_g2) */
     float acc_ms[5];
     float assemble_kernel_ms; /* k_assemble_post alone (assemble_ms also covers the proof read-back) */
-    float _reserved[2];
+    float h_wait_ms;  /* end of the witness-map slot -> start of the h MSM on the main stream (staggered plan: the h scatter) */
+    float h_start_ms; /* start of the call -> start of the h MSM */
 } g16_timings;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------------- */
@@ -136,6 +137,12 @@ const char* g16_version(void);
  * precompute != 0 additionally stores 2^(c*j) multiples of every base so that all Pippenger windows share one bucket
  * set (trades HBM for the per-window reduction and the Horner tail). */
 int g16_ctx_load_pk(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int shard_count, int precompute);
+/* Same with explicit ranges instead of the uniform split: h_range = [lo, hi) of h_query, z_range = [lo, hi) of the wire
+ * index space of a_query[1..] / b_g1_query[1..] / b_g2_query[1..] (l_query follows a's range).  The ranks' ranges must
+ * partition each query; an empty range is allowed.  Used by the staggered plan (g16_prove_shard_begin_dev below): the
+ * rank that runs the witness map takes a smaller share of the wire MSMs. */
+int g16_ctx_load_pk_ranges(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, int shard_count, const uint64_t h_range[2],
+                           const uint64_t z_range[2], int precompute);
 /* Uploads the R1CS matrices (once; proof-independent -- SURVEY 8f-1). */
 int g16_ctx_load_r1cs(g16_ctx* ctx, const g16_r1cs_view* r1cs);
 
@@ -156,6 +163,14 @@ int g16_prove_combine(g16_ctx* ctx, const g16_partial* partials, int count, cons
 int g16_partial_dev(g16_ctx* ctx, void** dev_ptr, size_t* bytes);
 int g16_prove_shard_dev(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], int reduction); /* witness resident; result left in the device partial */
 int g16_copy_partial_dev(g16_ctx* ctx, void* dst_dev);         /* stream-ordered D2D copy of the partial (e.g. into an NCCL buffer) */
+/* g16_prove_shard_dev in two halves, for the staggered multi-GPU plan: only ONE rank runs the witness map
+ * (run_witness_map != 0) while the others spend that time on their larger share of the wire MSMs; the host glue then
+ * scatters h (g16_copy_h_dev into the collective's buffer, one NCCL scatter on the context's main stream) and every rank
+ * finishes with the h MSM over its h range, reading the coefficients h[h_first, h_first + h_count) from h_dev (Montgomery
+ * Fr; must cover the rank's h range; NULL = this context's own witness-map output).  begin: forks the wire MSMs (+ witness map); finish: h MSM + join; the partial is then in the device buffer. */
+int g16_prove_shard_begin_dev(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], int reduction, int run_witness_map);
+int g16_prove_shard_finish_dev(g16_ctx* ctx, const void* h_dev, size_t h_first, size_t h_count); /* h_dev[i] = h[h_first + i], i < h_count */
+int g16_copy_h_dev(g16_ctx* ctx, void* dst_dev, size_t capacity_elems); /* stream-ordered D2D copy of h (n elements) */
 /* Optional, rank 0: starts the (r, s, pk)-only scalar multiplications on a side stream so that they overlap the shard work;
  * a later g16_prove_combine[_dev] with the same (r, s) joins them instead of running them serially. */
 int g16_prove_prepare(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4]);

@@ -35,3 +35,57 @@ def test_sharded_prove_matches_golden(name, world):
     finally:
         for ctx in ctxs:
             ctx.close()
+
+
+@pytest.mark.parametrize("name,world,share", [("rand300", 2, None), ("rand300", 3, 0.0), ("dummy924_nozk", 4, 0.3),
+                                              ("rand100", 8, None), ("rand100_circom", 2, 1.0)])
+def test_staggered_plan_matches_golden(name, world, share):
+    """Staggered plan (sharded.py): only rank 0 runs the witness map, the other ranks take a larger share of the wire MSMs
+    and receive their h chunk; G contexts on one device play the ranks and a device copy plays the NCCL scatter.
+    share = 0.0 leaves rank 0 with EMPTY a / l / b ranges, share = 1.0 leaves every other rank with empty ones."""
+    from crescent_credentials_b200.sharded import staggered_plan
+    meta, r1cs_bytes, pk_bytes = load_golden(name)
+    mats = load_matrices(r1cs_bytes)
+    pk = g.ProvingKey.deserialize_uncompressed_unchecked(pk_bytes)
+    wires = mats.num_instance_variables + mats.num_witness_variables
+    z = g.fr_to_mont([int(v, 16) for v in meta["z"]])
+    reduction = ffi.REDUCTION_CIRCOM if meta.get("reduction") == "circom" else ffi.REDUCTION_LIBSNARK
+    h_len = np.asarray(pk.arrays["h_query"]).reshape(-1, 8).shape[0]
+    m1 = np.asarray(pk.arrays["a_query"]).reshape(-1, 8).shape[0] - 1
+    plan = staggered_plan(h_len, m1, world, share)
+    assert plan.z_ranges[0][0] == 0 and plan.z_ranges[-1][1] == m1 and plan.h_ranges[-1][1] == h_len
+    parts, ctxs = [], []
+    try:
+        for rank in range(world):
+            ctx = ffi.Context(0)
+            ctxs.append(ctx)
+            ctx.load_r1cs(mats.num_constraints, mats.num_instance_variables, wires, mats.row_ptr, mats.col, mats.val, mats.encoding)
+            ctx.load_pk(pk.arrays, pk.encoding, rank, world, h_range=plan.h_ranges[rank], z_range=plan.z_ranges[rank])
+            ctx.upload_witness(z)
+        r, s = g.fr_to_mont([int(meta["r"], 16)])[0], g.fr_to_mont([int(meta["s"], 16)])[0]
+        n = ctxs[0].domain_size()
+        cap = max(n, world * plan.h_chunk)
+        h_all = ctxs[0].dev_alloc(cap * 32)
+        for rank, ctx in enumerate(ctxs):
+            ctx.prove_shard_begin_dev(r, s, reduction, run_witness_map=(rank == 0))
+        ctxs[0].copy_h_dev(h_all, cap)
+        ctxs[0].sync()
+        for rank, ctx in enumerate(ctxs):
+            if rank == 0:
+                ctx.prove_shard_finish_dev()
+            else:   # the chunk this rank would receive from the scatter
+                ctx.prove_shard_finish_dev(h_all + rank * plan.h_chunk * 32, plan.h_ranges[rank][0], plan.h_chunk)
+            ptr, nbytes = ctx.partial_dev()
+            ctx.sync()
+            parts.append(ctx.dev_download(ptr, np.zeros(nbytes // 8, dtype=np.uint64)))
+        proof = g.Proof.from_ffi(ctxs[0].prove_combine(np.stack(parts), r, s))
+        assert proof.serialize_uncompressed().hex() == meta["proof_uncompressed"]
+        with pytest.raises(ffi.G16Error):   # finish without begin
+            ctxs[0].prove_shard_finish_dev()
+        ctxs[0].prove_shard_begin_dev(r, s, reduction, run_witness_map=False)
+        with pytest.raises(ffi.G16Error):   # h chunk that does not cover the rank's range
+            ctxs[0].prove_shard_finish_dev(h_all, plan.h_ranges[0][1] + 1, 1)
+        ctxs[0].dev_free(h_all)
+    finally:
+        for ctx in ctxs:
+            ctx.close()

@@ -114,6 +114,69 @@ def test_two_rank_gloo_gather_of_partials():
     assert got == [1, 2, (2, ffi.PARTIAL_U64)]
 
 
+def test_staggered_plan_partitions_every_query():
+    """sharded.staggered_plan: rank 0 (the witness-map rank) gets the share f0 of the wire MSMs, the rest is split evenly;
+    h is cut in equal scatter chunks.  Whatever f0, the ranges must partition the queries."""
+    from crescent_credentials_b200.sharded import rank0_wire_share, staggered_plan
+    for h_len, m1 in ((0, 1), (7, 5), (1023, 923), (2_097_151, 1_449_999)):
+        for world in (1, 2, 3, 4, 8):
+            for share in (None, 0.0, 0.25, 1.0):
+                plan = staggered_plan(h_len, m1, world, share)
+                for spans, total in ((plan.z_ranges, m1), (plan.h_ranges, h_len)):
+                    assert len(spans) == world and spans[0][0] == 0 and spans[-1][1] == total
+                    assert all(lo <= hi for lo, hi in spans)
+                    assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+                if world > 1:
+                    assert plan.wm_rank == 0 and plan.h_chunk * world >= h_len
+                    assert all(hi - lo <= plan.h_chunk and lo == min(r * plan.h_chunk, h_len) for r, (lo, hi) in enumerate(plan.h_ranges))
+                    if share is not None:
+                        assert plan.z_ranges[0][1] == round(m1 * share)
+    # the balance point: wm + f0 Z == (1 - f0) Z / (G - 1); no wire work for rank 0 once Z / (G - 1) < wm
+    assert rank0_wire_share(1) == 1.0
+    f2 = rank0_wire_share(2, 0.25)
+    assert abs((0.25 + f2) - (1 - f2)) < 1e-12
+    assert rank0_wire_share(8, 0.25) == 0.0
+
+
+def _gloo_scatter_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from crescent_credentials_b200.sharded import scatter_h, staggered_plan
+    h_len = 13
+    plan = staggered_plan(h_len, 9, world)
+    h_all = None
+    if rank == plan.wm_rank:   # n = 16 coefficients of 4 words; coefficient i is [4i, 4i+1, 4i+2, 4i+3]
+        h_all = torch.arange(max(16, world * plan.h_chunk) * 4, dtype=torch.int64).view(-1, 4)
+    h_mine = torch.zeros((plan.h_chunk, 4), dtype=torch.int64)
+    scatter_h(h_all, h_mine, plan, rank)
+    lo, hi = plan.h_ranges[rank]
+    q.put((rank, lo, hi, [int(v) for v in h_mine[:hi - lo, 0]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_scatter_of_h_chunks():
+    """The one extra collective of the staggered plan: every rank receives exactly the h coefficients of its h range."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_scatter_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert [(lo, hi) for _, lo, hi, _ in got] == [(0, 7), (7, 13)]
+    for _, lo, hi, first_words in got:
+        assert first_words == [4 * i for i in range(lo, hi)]
+
+
 def test_sharded_msm_partials_add_up_on_cpu():
     """The sharding identity the multi-GPU path relies on: MSM over [0,N) == sum of MSMs over the rank ranges
     (checked with the CPU oracle; the GPU version of this test is in test_gpu_sharded.py)."""
