@@ -79,6 +79,13 @@ int g16_ctx_create(g16_ctx** out, int device, void* main_stream) {
         e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     }
+    if (e == cudaSuccess) {
+        int lo = 0, hi = 0;  // numerically lower = higher priority
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->hi, cudaStreamNonBlocking, hi);
+    }
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_dig[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_hi, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_scale[i], cudaEventDisableTiming);
     for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev_t[i]);
@@ -100,6 +107,7 @@ static void free_r1cs(g16_ctx* ctx) {
         dev_free(ctx->mat[k].row_ptr);
         dev_free(ctx->mat[k].col);
         dev_free(ctx->mat[k].val);
+        sell_free(&ctx->mat[k]);
         ctx->mat[k] = CsrDev();
     }
     dev_free(ctx->d_z);
@@ -135,6 +143,10 @@ void g16_ctx_destroy(g16_ctx* ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->hi) cudaStreamDestroy(ctx->hi);
+    if (ctx->ev_hi) cudaEventDestroy(ctx->ev_hi);
+    for (int i = 0; i < 2; i++)
+        if (ctx->ev_dig[i]) cudaEventDestroy(ctx->ev_dig[i]);
     for (int i = 0; i < 2; i++)
         if (ctx->ev_scale[i]) cudaEventDestroy(ctx->ev_scale[i]);
     for (int i = 0; i < 16; i++)
@@ -388,6 +400,7 @@ int g16_ctx_load_r1cs(g16_ctx* ctx, const g16_r1cs_view* v) {
             G16_CUDA(ctx, cudaMemcpyAsync(ctx->mat[k].val, v->val[k], nnz * 32, cudaMemcpyHostToDevice, ctx->main));
             if (v->encoding == G16_ENC_CANONICAL) G16_TRY(convert_mont_dev(ctx, G16_FIELD_FR, ctx->mat[k].val, nnz, true, ctx->main));
         }
+        if (ctx->nc && ctx->m < ((uint64_t)1 << 30)) G16_TRY(sell_build(ctx, k, v->row_ptr[k], ctx->main));
     }
     G16_TRY(dev_alloc(ctx, &ctx->d_z, ctx->m));
     G16_TRY(dev_alloc(ctx, &ctx->d_a, n));
@@ -615,7 +628,7 @@ struct PartialLayout {
 // Split in two so that a rank which does not run the witness map itself can receive h between the halves:
 //   shard_begin  forks the z-only MSMs onto the side streams and (run_wm) runs the witness map on main;
 //   shard_finish runs the h MSM on main over h_src (NULL = the witness map's own output) and joins the side streams.
-static int shard_begin(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int reduction, bool run_wm) {
+static int shard_begin(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int reduction, bool run_wm, bool allow_hi = false) {
     cudaStream_t main = ctx->main;
     PartialLayout* part = (PartialLayout*)ctx->d_partial;
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
@@ -650,11 +663,24 @@ static int shard_begin(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int r
     bool* scaled = ctx->sh_scaled;
     scaled[0] = scaled[1] = false;
     ctx->sh_nchains = nchains;
+    ctx->sh_join_mask = 0;
+    int nsplit = 0;
     for (int k = 0; k < nchains; k++) {
-        cudaStream_t st = ctx->opt_serialize ? main : ctx->side[k];
-        if (!ctx->opt_serialize) G16_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+        cudaStream_t st0 = ctx->opt_serialize ? main : ctx->side[k];
+        if (!ctx->opt_serialize) G16_CUDA(ctx, cudaStreamWaitEvent(st0, ctx->ev_fork, 0));
+        // split chain: the MSM that reuses the digit stage starts on its own stream as soon as that stage exists, instead of
+        // queueing behind the first MSM's point stage (a serial chain left the G2 MSM alone at the end of the proof)
+        const bool split = chain_len[k] == 2 && ctx->opt_split_chains && !ctx->opt_serialize;
+        const int split_slot = split ? nsplit++ : -1;
         for (int j = 0; j < chain_len[k]; j++) {
             int qi = chains[k][j].qi, from = chains[k][j].from;
+            cudaStream_t st = st0;
+            int join_idx = k;
+            if (split && j == 1) {
+                st = ctx->side[7 + split_slot];
+                join_idx = 7 + split_slot;
+                G16_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_dig[split_slot], 0));
+            }
             cudaEvent_t ea0 = ctx->opt_kernel_events ? ctx->ev_acc[2 * qi] : nullptr;
             cudaEvent_t ea1 = ctx->opt_kernel_events ? ctx->ev_acc[2 * qi + 1] : nullptr;
             const Fr* sc;
@@ -667,7 +693,9 @@ static int shard_begin(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int r
                 cnt = ctx->sh_hi[qi] - ctx->sh_lo[qi];
             }
             G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * qi], st));
-            G16_TRY(msm_run(ctx, &ctx->q[qi], &ctx->scratch[qi], sc, cnt, st, ea0, ea1, from >= 0 ? &ctx->scratch[from] : nullptr));
+            if (split && j == 0 && cnt == 0) G16_CUDA(ctx, cudaEventRecord(ctx->ev_dig[split_slot], st));  // nothing to build
+            G16_TRY(msm_run(ctx, &ctx->q[qi], &ctx->scratch[qi], sc, cnt, st, ea0, ea1, from >= 0 ? &ctx->scratch[from] : nullptr,
+                            split && j == 0 ? ctx->ev_dig[split_slot] : nullptr));
             const bool have = cnt && ctx->scratch[qi].result;
             // s * MSM_a and r * MSM_b1 are ~1.6 ms single-lane chains: they get their own streams so that neither the next
             // MSM of this chain nor anything else waits for them; they finish beside the MSMs still in flight
@@ -696,35 +724,51 @@ static int shard_begin(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int r
                 if (qi == Q_A) G16_TRY(scale_aside(0, s, &part->sa));  // s * MSM_a for s * g_a (prover.rs:98)
             }
             G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * qi], st));
+            if (!ctx->opt_serialize && (j + 1 == chain_len[k] || split)) {
+                G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[join_idx], st));
+                ctx->sh_join_mask |= 1u << join_idx;
+            }
         }
-        if (!ctx->opt_serialize) G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], st));
     }
     // main: witness map (r1cs_to_qap.rs:150-213)
-    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[0], main));
-    if (run_wm) G16_TRY(witness_map_dev(ctx, reduction, main));
-    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[1], main));
+    // (option wm_priority: on the high-priority twin of main, so that the h MSM -- which can only start afterwards -- is not
+    // pushed to the end of the proof by the four z-only MSMs already in flight)
+    cudaStream_t ws = (allow_hi && run_wm && ctx->opt_wm_priority && !ctx->opt_serialize && ctx->hi) ? ctx->hi : main;
+    ctx->sh_wm_stream = ws;
+    if (ws != main) G16_CUDA(ctx, cudaStreamWaitEvent(ws, ctx->ev_fork, 0));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[0], ws));
+    if (run_wm) G16_TRY(witness_map_dev(ctx, reduction, ws));
+    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[1], ws));
     return G16_OK;
 }
 
 static int shard_finish(g16_ctx* ctx, const Fr* h_src) {
     cudaStream_t main = ctx->main;
+    cudaStream_t hs = (!h_src && ctx->sh_wm_stream) ? ctx->sh_wm_stream : main;
     PartialLayout* part = (PartialLayout*)ctx->d_partial;
     const int nchains = ctx->sh_nchains;
     const bool* scaled = ctx->sh_scaled;
     // the h MSM over h[lo..hi)  (prover.rs:63-66; the zip drops h[n-1], generator.rs:178)
     {
         size_t cnt = ctx->sh_hi[Q_H] - ctx->sh_lo[Q_H];
-        G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * Q_H], main));
-        G16_TRY(msm_run(ctx, &ctx->q[Q_H], &ctx->scratch[Q_H], (h_src ? h_src : ctx->d_a) + ctx->sh_lo[Q_H], cnt, main,
+        G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[2 + 2 * Q_H], hs));
+        G16_TRY(msm_run(ctx, &ctx->q[Q_H], &ctx->scratch[Q_H], (h_src ? h_src : ctx->d_a) + ctx->sh_lo[Q_H], cnt, hs,
                         ctx->opt_kernel_events ? ctx->ev_acc[0] : nullptr, ctx->opt_kernel_events ? ctx->ev_acc[1] : nullptr));
         if (cnt && ctx->scratch[Q_H].result)
-            G16_CUDA(ctx, cudaMemcpyAsync(&part->h, ctx->scratch[Q_H].result, sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, main));
+            G16_CUDA(ctx, cudaMemcpyAsync(&part->h, ctx->scratch[Q_H].result, sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, hs));
         else
-            G16_CUDA(ctx, cudaMemsetAsync(&part->h, 0, sizeof(G1XYZZ), main));
-        G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * Q_H], main));
+            G16_CUDA(ctx, cudaMemsetAsync(&part->h, 0, sizeof(G1XYZZ), hs));
+        G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[3 + 2 * Q_H], hs));
     }
+    if (hs != main) {
+        G16_CUDA(ctx, cudaEventRecord(ctx->ev_hi, hs));
+        G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_hi, 0));
+    }
+    ctx->sh_wm_stream = nullptr;
     if (!ctx->opt_serialize) {
-        for (int k = 0; k < nchains; k++) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[k], 0));
+        (void)nchains;
+        for (int k = 0; k < kSideStreams; k++)
+            if (ctx->sh_join_mask & (1u << k)) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[k], 0));
         for (int k = 0; k < 2; k++)
             if (scaled[k]) G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[5 + k], 0));
     }
@@ -732,7 +776,7 @@ static int shard_finish(g16_ctx* ctx, const Fr* h_src) {
 }
 
 static int prove_shard_streams(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int reduction) {
-    G16_TRY(shard_begin(ctx, r, s, reduction, true));
+    G16_TRY(shard_begin(ctx, r, s, reduction, true, true));
     return shard_finish(ctx, nullptr);
 }
 
@@ -945,6 +989,10 @@ int g16_set_option(g16_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "acc_variant")) ctx->opt_acc_variant = value;
     else if (!strcmp(key, "ba_levels")) ctx->opt_ba_levels = value;
     else if (!strcmp(key, "share_digits")) ctx->opt_share_digits = value;
+    else if (!strcmp(key, "split_chains")) ctx->opt_split_chains = value;
+    else if (!strcmp(key, "ntt_radix4")) ctx->opt_ntt_radix4 = value;
+    else if (!strcmp(key, "spmv_sell")) ctx->opt_spmv_sell = value;
+    else if (!strcmp(key, "wm_priority")) ctx->opt_wm_priority = value;
     else return set_err(ctx, G16_ERR_BAD_ARG, "unknown option '%s'", key);
     return G16_OK;
 }

@@ -14,7 +14,7 @@
 
 namespace g16 {
 
-constexpr int kSideStreams = 7;  // 0-3 MSM chains, 4 (r, s)-only scalar multiplications, 5-6 s*MSM_a / r*MSM_b1
+constexpr int kSideStreams = 9;  // 0-3 MSM chains, 4 (r, s)-only scalar multiplications, 5-6 s*MSM_a / r*MSM_b1, 7-8 second MSM of a split chain
 constexpr int kMsmSlots = 8;
 constexpr int kNumSMs = 148;  // B200
 
@@ -85,7 +85,14 @@ struct CsrDev {
     uint32_t* col = nullptr;
     Fr* val = nullptr;
     size_t nnz = 0;
+    // sliced-ELL copy (witness.cu): rows sorted by length, 32 rows per slice, entries of a slice stored step-major
+    uint32_t* sell_row = nullptr;   // [slices * 32] row evaluated by every lane (kSellNoRow = none)
+    uint64_t* sell_ptr = nullptr;   // [slices + 1] first entry of every slice (multiples of 32)
+    uint32_t* sell_col = nullptr;   // [sell_ptr[slices]] column | coefficient class << 30
+    Fr* sell_val = nullptr;         // [sell_ptr[slices]] coefficient (read for class 0 only)
+    size_t slices = 0;
 };
+constexpr uint32_t kSellNoRow = 0xFFFFFFFFu;
 
 }  // namespace g16
 
@@ -129,7 +136,15 @@ struct g16_ctx {
     int opt_serialize = 0, opt_kernel_events = 0, opt_window_bits = 0, opt_acc_variant = 0;
     int opt_ba_levels = -1;  // batched-affine levels (-1 = default)
     int opt_share_digits = 1;
+    int opt_spmv_sell = 1;     // sliced-ELL SpMV (0: row-per-thread CSR kernel)
+    int opt_ntt_radix4 = 1;    // two butterfly levels per shared-memory round trip (k_ntt_pass4)
+    int opt_split_chains = 1;  // the MSM that reuses a digit stage runs beside the one that built it, not after it
+    int opt_wm_priority = 0;   // witness map + h MSM on the internal high-priority stream
+    cudaStream_t hi = nullptr;  // high-priority twin of main
+    cudaEvent_t ev_dig[2] = {}, ev_hi = nullptr;
     bool share_al = false, share_b = false;  // l reuses a's digit stage / b_g2 reuses b_g1's
+    cudaStream_t sh_wm_stream = nullptr;      // stream the witness map of the open shard run was queued on
+    uint32_t sh_join_mask = 0;                // ev_join[] entries shard_finish has to wait for
     int sh_nchains = 0;                       // state handed from shard_begin to shard_finish (api.cu)
     bool sh_scaled[2] = {false, false};
     bool shard_open = false;
@@ -199,6 +214,9 @@ int ntt_api(g16_ctx* ctx, Fr* data_dev, unsigned log_n, int inverse, int coset, 
 // witness.cu ------------------------------------------------------------------------------------------------------------
 int witness_map_dev(g16_ctx* ctx, int reduction, cudaStream_t st);  // z in ctx->d_z; h left in ctx->d_a (natural order)
 int r1cs_eval_dev(g16_ctx* ctx, Fr* az, Fr* bz, Fr* cz, bool bitrev, cudaStream_t st);
+// builds the sliced-ELL copy of matrix k from its CSR arrays (host row_ptr for the row order, device col / val for the entries)
+int sell_build(g16_ctx* ctx, int k, const uint64_t* row_ptr_host, cudaStream_t st);
+void sell_free(CsrDev* m);
 
 // msm.cu ----------------------------------------------------------------------------------------------------------------
 int msm_pick_window(size_t n, int group, bool precomp);
@@ -209,7 +227,8 @@ void msm_free(MsmBases* mb, MsmScratch* sc);
 // `digits` (optional): scratch of another MSM that already ran over the SAME scalars on this stream, with the same
 // n / window / table geometry and skip pattern (msm_can_share): its sorted references and task lists are reused.
 int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st,
-            cudaEvent_t ev_acc0 = nullptr, cudaEvent_t ev_acc1 = nullptr, const MsmScratch* digits = nullptr);
+            cudaEvent_t ev_acc0 = nullptr, cudaEvent_t ev_acc1 = nullptr, const MsmScratch* digits = nullptr,
+            cudaEvent_t ev_digits_done = nullptr);  // recorded on st once the digit stage this call built is complete
 // true when MSMs over `b` may reuse the digit stage of `a` (same geometry; every point `a` skips is infinity in `b` too
 // and `b` has at most `max_extra_inf` further points at infinity).  Synchronises the stream.
 int msm_can_share(g16_ctx* ctx, const MsmBases* a, const MsmBases* b, size_t max_extra_inf, bool* ok, cudaStream_t st);

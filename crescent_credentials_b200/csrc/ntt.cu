@@ -213,6 +213,164 @@ __global__ void __launch_bounds__(kNttThreads, 2)
     }
 }
 
+// ---- the same pass with two butterfly levels per shared-memory round trip ---------------------------------------------
+// A thread keeps the four elements whose row indices differ in bits q and q+1 in registers and runs levels q and q+1 on
+// them (4 products, as two radix-2 levels would: in a prime field the fourth root of unity is no cheaper than any other
+// twiddle).  Halves the shared-memory traffic, the barriers and the index arithmetic of the radix-2 loop; an odd level
+// count leaves one radix-2 level.  Results are bit-identical to k_ntt_pass (exact arithmetic, same twiddle table).
+constexpr int kNtt4Threads = 256;
+
+__device__ __forceinline__ Fr sm_ld(const uint4* lo, const uint4* hi, unsigned i) {
+    Fr x;
+    *reinterpret_cast<uint4*>(&x.v[0]) = lo[i];
+    *reinterpret_cast<uint4*>(&x.v[4]) = hi[i];
+    return x;
+}
+__device__ __forceinline__ void sm_st(uint4* lo, uint4* hi, unsigned i, const Fr& x) {
+    lo[i] = *reinterpret_cast<const uint4*>(&x.v[0]);
+    hi[i] = *reinterpret_cast<const uint4*>(&x.v[4]);
+}
+__device__ __forceinline__ Fr tw_ld(const Fr* p) {
+    Fr w;
+    const uint4* wp = reinterpret_cast<const uint4*>(p);
+    *reinterpret_cast<uint4*>(&w.v[0]) = __ldg(wp);
+    *reinterpret_cast<uint4*>(&w.v[4]) = __ldg(wp + 1);
+    return w;
+}
+
+template <bool DIT>
+__global__ void __launch_bounds__(kNtt4Threads, 3)
+    k_ntt_pass4(Fr* __restrict__ data, const Fr* __restrict__ tw, unsigned log_n, unsigned s_lo, unsigned nlev,
+                unsigned t_log, const Fr* __restrict__ pre, const Fr* __restrict__ post, Fr post_scalar,
+                int has_post_scalar, const Fr* __restrict__ sub) {
+    extern __shared__ uint4 smem[];
+    const unsigned tile_log = nlev + t_log;
+    const unsigned tile = 1u << tile_log;
+    uint4* sm_lo = smem;
+    uint4* sm_hi = smem + tile;
+    const unsigned T = 1u << t_log;
+    const size_t blk = blockIdx.x;
+    const size_t lo_tiles = (size_t)1 << (s_lo - t_log);
+    const size_t lo_base = (blk % lo_tiles) << t_log;
+    const size_t hi = blk / lo_tiles;
+    const size_t gbase = (hi << (s_lo + nlev)) | lo_base;
+
+    for (unsigned e = threadIdx.x; e < tile; e += kNtt4Threads) {
+        unsigned c = e & (T - 1), j = e >> t_log;
+        size_t gi = gbase | ((size_t)j << s_lo) | c;
+        const uint4* src = reinterpret_cast<const uint4*>(data + gi);
+        uint4 a = src[0], b = src[1];
+        if (pre) {
+            Fr x, p = pre[gi];
+            *reinterpret_cast<uint4*>(&x.v[0]) = a;
+            *reinterpret_cast<uint4*>(&x.v[4]) = b;
+            x = x * p;
+            a = *reinterpret_cast<uint4*>(&x.v[0]);
+            b = *reinterpret_cast<uint4*>(&x.v[4]);
+        }
+        sm_lo[e] = a;
+        sm_hi[e] = b;
+    }
+    __syncthreads();
+
+    // one radix-2 level q (the leftover of an odd level count)
+    auto radix2 = [&](unsigned q) {
+        const unsigned s = s_lo + q;
+        const unsigned tw_shift = log_n - s - 1;
+        for (unsigned bf = threadIdx.x; bf < (tile >> 1); bf += kNtt4Threads) {
+            unsigned c = bf & (T - 1), jb = bf >> t_log;
+            unsigned jl = jb & ((1u << q) - 1);
+            unsigned j0 = ((jb >> q) << (q + 1)) | jl;
+            unsigned i0 = (j0 << t_log) | c;
+            unsigned i1 = i0 | (1u << (q + t_log));
+            size_t low = ((size_t)jl << s_lo) | (lo_base + c);
+            Fr x = sm_ld(sm_lo, sm_hi, i0), y = sm_ld(sm_lo, sm_hi, i1);
+            Fr w = tw_ld(tw + (low << tw_shift));
+            Fr u, v;
+            if (DIT) {
+                Fr t = y * w;
+                u = x + t;
+                v = x - t;
+            } else {
+                u = x + y;
+                v = (x - y) * w;
+            }
+            sm_st(sm_lo, sm_hi, i0, u);
+            sm_st(sm_lo, sm_hi, i1, v);
+        }
+        __syncthreads();
+    };
+    // levels q and q + 1 together
+    auto radix4 = [&](unsigned q) {
+        const unsigned s = s_lo + q;
+        const unsigned sh1 = log_n - s - 1, sh2 = log_n - s - 2;
+        for (unsigned g = threadIdx.x; g < (tile >> 2); g += kNtt4Threads) {
+            unsigned c = g & (T - 1), jb = g >> t_log;
+            unsigned jl = jb & ((1u << q) - 1);
+            unsigned j00 = ((jb >> q) << (q + 2)) | jl;
+            unsigned i00 = (j00 << t_log) | c;
+            unsigned b0 = 1u << (q + t_log), b1 = b0 << 1;
+            size_t low = ((size_t)jl << s_lo) | (lo_base + c);  // (global index of i00) mod 2^s
+            const Fr* w1p = tw + (low << sh1);                          // level s, both pairs
+            const Fr* w2ap = tw + (low << sh2);                         // level s + 1, pair (00, 10)
+            const Fr* w2bp = tw + ((low + ((size_t)1 << s)) << sh2);    // level s + 1, pair (01, 11)
+            if (DIT) {
+                Fr w1 = tw_ld(w1p);
+                Fr t1 = sm_ld(sm_lo, sm_hi, i00 | b0) * w1;
+                Fr t3 = sm_ld(sm_lo, sm_hi, i00 | b0 | b1) * w1;
+                Fr e0 = sm_ld(sm_lo, sm_hi, i00), e2 = sm_ld(sm_lo, sm_hi, i00 | b1);
+                Fr a0 = e0 + t1, a1 = e0 - t1, a2 = e2 + t3, a3 = e2 - t3;
+                Fr u = a2 * tw_ld(w2ap);
+                sm_st(sm_lo, sm_hi, i00, a0 + u);
+                sm_st(sm_lo, sm_hi, i00 | b1, a0 - u);
+                Fr v = a3 * tw_ld(w2bp);
+                sm_st(sm_lo, sm_hi, i00 | b0, a1 + v);
+                sm_st(sm_lo, sm_hi, i00 | b0 | b1, a1 - v);
+            } else {
+                Fr e0 = sm_ld(sm_lo, sm_hi, i00), e2 = sm_ld(sm_lo, sm_hi, i00 | b1);
+                Fr u0 = e0 + e2;
+                Fr d0 = (e0 - e2) * tw_ld(w2ap);
+                Fr e1 = sm_ld(sm_lo, sm_hi, i00 | b0), e3 = sm_ld(sm_lo, sm_hi, i00 | b0 | b1);
+                Fr u1 = e1 + e3;
+                Fr d1 = (e1 - e3) * tw_ld(w2bp);
+                Fr w1 = tw_ld(w1p);
+                sm_st(sm_lo, sm_hi, i00, u0 + u1);
+                sm_st(sm_lo, sm_hi, i00 | b0, (u0 - u1) * w1);
+                sm_st(sm_lo, sm_hi, i00 | b1, d0 + d1);
+                sm_st(sm_lo, sm_hi, i00 | b0 | b1, (d0 - d1) * w1);
+            }
+        }
+        __syncthreads();
+    };
+    if (DIT) {  // ascending levels
+        unsigned q = 0;
+        for (; q + 1 < nlev; q += 2) radix4(q);
+        if (q < nlev) radix2(q);
+    } else {  // descending levels
+        unsigned q = nlev;
+        for (; q >= 2; q -= 2) radix4(q - 2);
+        if (q == 1) radix2(0);
+    }
+
+    for (unsigned e = threadIdx.x; e < tile; e += kNtt4Threads) {
+        unsigned c = e & (T - 1), j = e >> t_log;
+        size_t gi = gbase | ((size_t)j << s_lo) | c;
+        uint4 a = sm_lo[e], b = sm_hi[e];
+        if (post || has_post_scalar) {
+            Fr x;
+            *reinterpret_cast<uint4*>(&x.v[0]) = a;
+            *reinterpret_cast<uint4*>(&x.v[4]) = b;
+            x = x * (post ? post[gi] : post_scalar);
+            if (sub) x = x - sub[gi];
+            a = *reinterpret_cast<uint4*>(&x.v[0]);
+            b = *reinterpret_cast<uint4*>(&x.v[4]);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(data + gi);
+        dst[0] = a;
+        dst[1] = b;
+    }
+}
+
 // the element-wise part of a transform when there is no butterfly to ride on (n == 1)
 __global__ void k_scale_table(Fr* __restrict__ data, const Fr* __restrict__ pre, const Fr* __restrict__ tbl, Fr scalar,
                               int scale, const Fr* __restrict__ sub, size_t n) {
@@ -258,6 +416,8 @@ static int ensure_smem_attr(g16_ctx* ctx) {
     size_t bytes = ((size_t)1 << kTileLog) * 32;
     G16_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     G16_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    G16_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    G16_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     g_smem_attr_set = true;
     return G16_OK;
 }
@@ -278,9 +438,14 @@ int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* p
         bool last = (k + 1 == passes.size());
         size_t blocks = ((size_t)1 << t->log_n) >> (p.nlev + p.t_log);
         size_t smem = ((size_t)1 << (p.nlev + p.t_log)) * 32;
-        G16_LAUNCH(ctx, k_ntt_pass<true>, (unsigned)blocks, kNttThreads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
-                   p.t_log, k == 0 ? pre_mul : (const Fr*)nullptr, last ? post : (const Fr*)nullptr, ps,
-                   (int)(last && post_scalar != nullptr && post == nullptr), last ? post_sub : (const Fr*)nullptr);
+        if (ctx->opt_ntt_radix4)
+            G16_LAUNCH(ctx, k_ntt_pass4<true>, (unsigned)blocks, kNtt4Threads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
+                       p.t_log, k == 0 ? pre_mul : (const Fr*)nullptr, last ? post : (const Fr*)nullptr, ps,
+                       (int)(last && post_scalar != nullptr && post == nullptr), last ? post_sub : (const Fr*)nullptr);
+        else
+            G16_LAUNCH(ctx, k_ntt_pass<true>, (unsigned)blocks, kNttThreads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
+                       p.t_log, k == 0 ? pre_mul : (const Fr*)nullptr, last ? post : (const Fr*)nullptr, ps,
+                       (int)(last && post_scalar != nullptr && post == nullptr), last ? post_sub : (const Fr*)nullptr);
     }
     return G16_OK;
 }
@@ -294,8 +459,12 @@ int ntt_dif(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* p
         bool first = (k + 1 == passes.size());
         size_t blocks = ((size_t)1 << t->log_n) >> (p.nlev + p.t_log);
         size_t smem = ((size_t)1 << (p.nlev + p.t_log)) * 32;
-        G16_LAUNCH(ctx, k_ntt_pass<false>, (unsigned)blocks, kNttThreads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
-                   p.t_log, first ? pre : (const Fr*)nullptr, (const Fr*)nullptr, Fr::zero(), 0, (const Fr*)nullptr);
+        if (ctx->opt_ntt_radix4)
+            G16_LAUNCH(ctx, k_ntt_pass4<false>, (unsigned)blocks, kNtt4Threads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
+                       p.t_log, first ? pre : (const Fr*)nullptr, (const Fr*)nullptr, Fr::zero(), 0, (const Fr*)nullptr);
+        else
+            G16_LAUNCH(ctx, k_ntt_pass<false>, (unsigned)blocks, kNttThreads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
+                       p.t_log, first ? pre : (const Fr*)nullptr, (const Fr*)nullptr, Fr::zero(), 0, (const Fr*)nullptr);
     }
     return G16_OK;
 }

@@ -64,6 +64,26 @@ def test_ntt_matches_oracle(gpu_ctx, log_n):
     assert g.fr_from_mont(gpu_ctx.ntt(x, inverse=True, coset=True)) == dom.coset_ifft(vals)
 
 
+@pytest.mark.parametrize("log_n", [4, 11, 14, 21, 22, 23])
+def test_ntt_radix4_pass_equals_radix2_pass(gpu_ctx, log_n):
+    """k_ntt_pass4 (two levels per shared-memory round trip) against k_ntt_pass (one level): identical bits for every
+    transform kind, including the multi-pass sizes whose tiles have column bits (t_log > 0) and odd level counts."""
+    n = 1 << log_n
+    rng = np.random.default_rng(100 + log_n)
+    x = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    x = gpu_ctx.field_op(ffi.FIELD_FR, ffi.OP_TO_MONT, gpu_ctx.field_op(ffi.FIELD_FR, ffi.OP_FROM_MONT, x))
+    try:
+        for inverse in (False, True):
+            for coset in (False, True):
+                gpu_ctx.set_option("ntt_radix4", 0)
+                want = gpu_ctx.ntt(x, inverse=inverse, coset=coset)
+                gpu_ctx.set_option("ntt_radix4", 1)
+                got = gpu_ctx.ntt(x, inverse=inverse, coset=coset)
+                assert np.array_equal(got, want), (log_n, inverse, coset)
+    finally:
+        gpu_ctx.set_option("ntt_radix4", 1)
+
+
 @pytest.mark.parametrize("log_n", [16, 20])
 def test_ntt_round_trip_large(gpu_ctx, log_n):
     n = 1 << log_n
@@ -291,3 +311,60 @@ def test_golden_prove_digit_sharing(share, levels):
             assert proof.serialize_uncompressed().hex() == meta["proof_uncompressed"]
         finally:
             prover.close()
+
+
+@pytest.mark.parametrize("split,prio", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_golden_prove_stream_plans(split, prio):
+    """Where the MSMs are queued (the digit-sharing MSM beside / behind the one that built the stage; witness map + h MSM on
+    the high-priority stream) changes the order of execution only: same proof bytes, also when proofs run back to back."""
+    for name in ("rand300", "dummy924_nozk", "silly"):
+        meta, r1cs_bytes, pk_bytes = load_golden(name)
+        mats = load_matrices(r1cs_bytes)
+        pk = g.ProvingKey.deserialize_uncompressed_unchecked(pk_bytes)
+        prover = g.Groth16(0, precompute=True)
+        prover.ctx.set_option("share_digits", 1)
+        prover.ctx.set_option("split_chains", split)
+        prover.ctx.set_option("wm_priority", prio)
+        try:
+            z = [int(v, 16) for v in meta["z"]]
+            for _ in range(3):
+                proof = prover.create_proof_with_reduction_and_matrices(pk, int(meta["r"], 16), int(meta["s"], 16), mats,
+                                                                        mats.num_instance_variables, mats.num_constraints, z)
+                assert proof.serialize_uncompressed().hex() == meta["proof_uncompressed"]
+        finally:
+            prover.close()
+
+
+def test_spmv_sliced_ell_ragged_rows(gpu_ctx):
+    """Sliced-ELL SpMV (rows sorted by length, 32 per slice, +1 / -1 classes in the column word) against the oracle's
+    evaluate_constraint and against the row-per-thread CSR kernel: empty rows, rows longer than a slice, repeated wires in
+    a row, +1 / -1 / 0 / general coefficients, a row count that is not a multiple of 32; natural and bit-reversed order."""
+    rnd = random.Random(77)
+    R = o.R_MOD
+    m, nc, ni = 257, 101, 3
+    lens = [0, 1, 2, 33, 300, 64, 0, 5] + [rnd.choice([0, 1, 2, 3, 4, 7, 40]) for _ in range(nc - 8)]
+    pool = [1, R - 1, 0, 2, R - 2, 1 << 120, rnd.randrange(R), rnd.randrange(R)]
+    rows = [[(rnd.choice(pool) if rnd.random() < 0.8 else rnd.randrange(R), rnd.randrange(m)) for _ in range(L)] for L in lens]
+    ptr = np.zeros(nc + 1, dtype=np.uint64)
+    ptr[1:] = np.cumsum(lens)
+    col = np.array([c for r in rows for _, c in r], dtype=np.uint32)
+    val = g.fr_to_mont([v for r in rows for v, _ in r]).reshape(-1, 4)
+    z = [1] + [rnd.randrange(R) for _ in range(m - 1)]
+    zm = g.fr_to_mont(z)
+    want = [o.evaluate_constraint(r, z) for r in rows]
+    ctx = ffi.Context(0)
+    try:
+        ctx.load_r1cs(nc, ni, m, [ptr] * 3, [col] * 3, [val] * 3, ffi.ENC_MONTGOMERY)
+        for sell in (1, 0):
+            ctx.set_option("spmv_sell", sell)
+            az, bz, cz = ctx.r1cs_eval(zm, nc)
+            assert g.fr_from_mont(az) == want and g.fr_from_mont(bz) == want and g.fr_from_mont(cz) == want, sell
+        # the witness map places rows bit-reversed and pads: both reductions, both kernels, same h
+        for red in (ffi.REDUCTION_LIBSNARK, ffi.REDUCTION_CIRCOM):
+            ctx.set_option("spmv_sell", 1)
+            h1 = ctx.witness_map(zm, red)
+            ctx.set_option("spmv_sell", 0)
+            h0 = ctx.witness_map(zm, red)
+            assert np.array_equal(h0, h1), red
+    finally:
+        ctx.close()

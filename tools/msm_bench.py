@@ -23,12 +23,15 @@ ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--check", type=int, default=1)
 ap.add_argument("--ntt", type=int, default=0)
+ap.add_argument("--opt", nargs="*", default=[], help="library options, key=value (e.g. ntt_radix4=0)")
 args = ap.parse_args()
 tstream = torch.cuda.Stream()
 torch.cuda.set_stream(tstream)
 ctx = ffi.Context(0, tstream.cuda_stream)
 ctx.set_option("kernel_events", 1)
 ctx.set_option("acc_variant", args.variant)
+for kv in args.opt:
+    ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 for logn in args.logn:
     n = 1 << logn
     if args.ntt:
@@ -47,7 +50,7 @@ for logn in args.logn:
             torch.cuda.synchronize()
             res[name] = e0.elapsed_time(e1) / args.reps
         ctx.dev_free(d)
-        print(json.dumps({"ntt_log_n": logn, "ms": res, "GBps_alg_1pass": 64.0 * n / (res["fwd"] * 1e-3) / 1e9,
+        print(json.dumps({"ntt_log_n": logn, "opt": args.opt, "ms": res, "GBps_alg_1pass": 64.0 * n / (res["fwd"] * 1e-3) / 1e9,
                           "gmul_per_s": (n / 2) * logn / (res["fwd"] * 1e-3) / 1e9}))
         continue
     ks = ctx.field_op(ffi.FIELD_FR, ffi.OP_TO_MONT, synth.uniform_fr_canonical(11, 1, n))
