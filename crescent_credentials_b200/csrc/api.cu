@@ -993,6 +993,7 @@ int g16_set_option(g16_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "ntt_radix4")) ctx->opt_ntt_radix4 = value;
     else if (!strcmp(key, "spmv_sell")) ctx->opt_spmv_sell = value;
     else if (!strcmp(key, "wm_priority")) ctx->opt_wm_priority = value;
+    else if (!strcmp(key, "ba_prefetch")) ctx->opt_ba_prefetch = value;
     else return set_err(ctx, G16_ERR_BAD_ARG, "unknown option '%s'", key);
     return G16_OK;
 }

@@ -137,9 +137,13 @@ struct g16_ctx {
     int opt_ba_levels = -1;  // batched-affine levels (-1 = default)
     int opt_share_digits = 1;
     int opt_spmv_sell = 1;     // sliced-ELL SpMV (0: row-per-thread CSR kernel)
-    int opt_ntt_radix4 = 1;    // two butterfly levels per shared-memory round trip (k_ntt_pass4)
+    int opt_ntt_radix4 = 0;    // two butterfly levels per shared-memory round trip (k_ntt_pass4): 3.32 vs 3.67 ms for the witness map
+                               // alone, but +1.1 ms per proof when the MSM chains run beside it (profiles/r01_sched_sweep_b.jsonl)
     int opt_split_chains = 1;  // the MSM that reuses a digit stage runs beside the one that built it, not after it
     int opt_wm_priority = 0;   // witness map + h MSM on the internal high-priority stream
+    int opt_ba_prefetch = 0;   // 1: k_ba_add_pf (next slot's operands in flight as cp.async), 2: prefetch.global.L2 of the next
+                               // slot's table lines.  Both measured SLOWER than the plain kernel (level 0 is bound by random
+                               // 128-byte DRAM granules, not by latency): kept for the A/B record only
     cudaStream_t hi = nullptr;  // high-priority twin of main
     cudaEvent_t ev_dig[2] = {}, ev_hi = nullptr;
     bool share_al = false, share_b = false;  // l reuses a's digit stage / b_g2 reuses b_g1's

@@ -23,6 +23,7 @@ ap.add_argument("--serialize", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--ba-levels", type=int, default=-1)
 ap.add_argument("--share-digits", type=int, default=1)
+ap.add_argument("--opt", nargs="*", default=[], help="library options, key=value (e.g. ba_prefetch=0)")
 args = ap.parse_args()
 tstream = torch.cuda.Stream()
 torch.cuda.set_stream(tstream)
@@ -39,6 +40,8 @@ s_m = g.fr_to_mont([0x0F0E0D0C0B0A09080706050403020100FFEEDDCCBBAA9988 % g.R_MOD
 ctx.upload_witness(inst.z_mont)
 ctx.set_option("serialize", args.serialize)
 ctx.set_option("kernel_events", 1)
+for kv in args.opt:
+    ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 for _ in range(2):
     ctx.prove_resident(r_m, s_m)
 torch.cuda.synchronize()

@@ -18,13 +18,14 @@ from bench import build_problem  # noqa: E402
 from crescent_credentials_b200 import ffi  # noqa: E402
 from crescent_credentials_b200 import groth16 as g  # noqa: E402
 
-DEFAULTS = {"split_chains": 1, "wm_priority": 0, "ntt_radix4": 1, "serialize": 0}
+DEFAULTS = {"split_chains": 1, "wm_priority": 0, "ntt_radix4": 0, "spmv_sell": 1, "ba_prefetch": 0, "serialize": 0}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="S-rs256")
 ap.add_argument("--witness", default="uniform")
 ap.add_argument("--precompute", type=int, default=1)
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--repeat", type=int, default=1, help="walk the list of combinations this many times (noise estimate)")
 ap.add_argument("--combos", default="split_chains=0,ntt_radix4=0;split_chains=1,ntt_radix4=0;split_chains=1,ntt_radix4=1;"
                                     "split_chains=1,ntt_radix4=1,wm_priority=1;split_chains=0,ntt_radix4=1,wm_priority=1")
 args = ap.parse_args()
@@ -38,7 +39,7 @@ r_m = g.fr_to_mont([0x1111222233334444555566667777888899990000AAAABBBBCCCCDDDD %
 s_m = g.fr_to_mont([0x0F0E0D0C0B0A09080706050403020100FFEEDDCCBBAA9988 % g.R_MOD])[0]  # same (r, s) as bench.py
 ctx.upload_witness(inst.z_mont)
 first = None
-for combo in args.combos.split(";"):
+for combo in args.combos.split(";") * args.repeat:
     opts = dict(DEFAULTS)
     for kv in combo.split(","):
         if kv.strip():
