@@ -737,7 +737,15 @@ static int shard_begin(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, int r
     ctx->sh_wm_stream = ws;
     if (ws != main) G16_CUDA(ctx, cudaStreamWaitEvent(ws, ctx->ev_fork, 0));
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[0], ws));
-    if (run_wm) G16_TRY(witness_map_dev(ctx, reduction, ws));
+    if (run_wm) {
+        // transforms beside MSM chains use the radix-2 passes, a lone witness map the radix-4 ones (see opt_ntt_radix4)
+        bool busy = false;
+        for (int qi : {Q_L, Q_A, Q_B1, Q_B2}) busy = busy || ctx->sh_hi[qi] > ctx->sh_lo[qi];
+        ctx->wm_alone = ctx->opt_serialize || !busy;
+        int rc = witness_map_dev(ctx, reduction, ws);
+        ctx->wm_alone = true;
+        G16_TRY(rc);
+    }
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[1], ws));
     return G16_OK;
 }

@@ -137,8 +137,11 @@ struct g16_ctx {
     int opt_ba_levels = -1;  // batched-affine levels (-1 = default)
     int opt_share_digits = 1;
     int opt_spmv_sell = 1;     // sliced-ELL SpMV (0: row-per-thread CSR kernel)
-    int opt_ntt_radix4 = 0;    // two butterfly levels per shared-memory round trip (k_ntt_pass4): 3.32 vs 3.67 ms for the witness map
-                               // alone, but +1.1 ms per proof when the MSM chains run beside it (profiles/r01_sched_sweep_b.jsonl)
+    int opt_ntt_radix4 = -1;   // k_ntt_pass4 (two butterfly levels per shared-memory round trip).  Alone it is faster (witness map
+                               // 3.32 vs 3.67 ms) but beside the MSM chains it costs +1.1 ms per proof (profiles/r01_sched_sweep_*):
+                               // -1 = auto: radix-4 when nothing runs beside the transforms (stand-alone calls, serialize, a
+                               // shard rank without wire MSM work), radix-2 passes otherwise; 0 / 1 force one kernel
+    bool wm_alone = true;      // state of the auto choice for the transforms being queued right now
     int opt_split_chains = 1;  // the MSM that reuses a digit stage runs beside the one that built it, not after it
     int opt_wm_priority = 0;   // witness map + h MSM on the internal high-priority stream
     int opt_ba_prefetch = 0;   // 1: k_ba_add_pf (next slot's operands in flight as cp.async), 2: prefetch.global.L2 of the next

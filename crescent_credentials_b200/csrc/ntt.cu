@@ -438,7 +438,7 @@ int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* p
         bool last = (k + 1 == passes.size());
         size_t blocks = ((size_t)1 << t->log_n) >> (p.nlev + p.t_log);
         size_t smem = ((size_t)1 << (p.nlev + p.t_log)) * 32;
-        if (ctx->opt_ntt_radix4)
+        if (ctx->opt_ntt_radix4 >= 0 ? ctx->opt_ntt_radix4 != 0 : ctx->wm_alone)
             G16_LAUNCH(ctx, k_ntt_pass4<true>, (unsigned)blocks, kNtt4Threads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
                        p.t_log, k == 0 ? pre_mul : (const Fr*)nullptr, last ? post : (const Fr*)nullptr, ps,
                        (int)(last && post_scalar != nullptr && post == nullptr), last ? post_sub : (const Fr*)nullptr);
@@ -459,7 +459,7 @@ int ntt_dif(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* p
         bool first = (k + 1 == passes.size());
         size_t blocks = ((size_t)1 << t->log_n) >> (p.nlev + p.t_log);
         size_t smem = ((size_t)1 << (p.nlev + p.t_log)) * 32;
-        if (ctx->opt_ntt_radix4)
+        if (ctx->opt_ntt_radix4 >= 0 ? ctx->opt_ntt_radix4 != 0 : ctx->wm_alone)
             G16_LAUNCH(ctx, k_ntt_pass4<false>, (unsigned)blocks, kNtt4Threads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
                        p.t_log, first ? pre : (const Fr*)nullptr, (const Fr*)nullptr, Fr::zero(), 0, (const Fr*)nullptr);
         else

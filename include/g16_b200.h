@@ -186,7 +186,13 @@ int g16_get_timings(g16_ctx* ctx, g16_timings* out);
  *   (fills g16_timings.acc_ms); = 2 brackets only the first level's k_ba_add launch (the dominant kernel),
  * "window_bits" = c forces the Pippenger window of bases loaded afterwards (0 = automatic),
  * "ba_levels" = L runs L pairwise batched-affine levels before the XYZZ tail for bases loaded afterwards (-1 = default 5,
- *   0 = XYZZ only), "share_digits" = 0 disables the reuse of one digit stage by a/l and b_g1/b_g2. */
+ *   0 = XYZZ only), "share_digits" = 0 disables the reuse of one digit stage by a/l and b_g1/b_g2,
+ * "split_chains" = 0 queues the MSM that reuses a digit stage behind the one that built it (default 1: beside it),
+ * "wm_priority" = 1 runs the witness map and the h MSM on a high-priority stream (default 0),
+ * "ntt_radix4" = 0 / 1 forces the radix-2 / radix-4 transform passes (default -1: radix-4 only when no MSM runs beside),
+ * "spmv_sell" = 0 selects the row-per-thread CSR kernel instead of the sliced-ELL one (default 1),
+ * "ba_prefetch" = 1 / 2 selects the cp.async / L2-prefetch variants of k_ba_add (default 0; both measured slower).
+ * No option changes a result bit.  Unknown keys return G16_ERR_BAD_ARG. */
 int g16_set_option(g16_ctx* ctx, const char* key, int value);
 
 /* ---- building blocks (parity hooks and the synthetic sweep) ------------------------------------------------------- */

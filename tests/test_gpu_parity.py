@@ -81,7 +81,7 @@ def test_ntt_radix4_pass_equals_radix2_pass(gpu_ctx, log_n):
                 got = gpu_ctx.ntt(x, inverse=inverse, coset=coset)
                 assert np.array_equal(got, want), (log_n, inverse, coset)
     finally:
-        gpu_ctx.set_option("ntt_radix4", 0)  # library default
+        gpu_ctx.set_option("ntt_radix4", -1)  # library default (auto)
 
 
 @pytest.mark.parametrize("log_n", [16, 20])
