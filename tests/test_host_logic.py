@@ -246,3 +246,19 @@ def test_sample_fr_with_stdrng_follows_fr_rand():
         if v < o.R_MOD:
             want.append(v * pow(1 << 256, -1, o.R_MOD) % o.R_MOD)
     assert got == want and len(set(got)) == 6
+
+
+def test_cpu_sample_scaling_follows_arkworks_window_rule():
+    """bench.py scales the CPU sample by ark-ec's addition count: window rule c = bit_length(n)*69//100 + 2 (3 below 32
+    pairs), ceil(254/c) windows of n + 2^c additions, one rayon task per window."""
+    import bench
+    assert bench.ark_msm_additions(0) == 0
+    assert bench.ark_msm_additions(16) == 85 * (16 + 2 * 4)                  # c = 3, 85 windows
+    n = 1 << 15                                                              # bit_length 16 -> c = 13, 20 windows
+    assert bench.ark_msm_additions(n) == 20 * (n + 2 * 4096)
+    full = 1_450_000                                                         # bit_length 21 -> c = 16, 16 windows
+    assert bench.ark_msm_additions(full) == 16 * (full + 2 * 32768)
+    assert bench.ark_msm_additions(full, threads=16) == full + 2 * 32768     # one round of windows on 16 threads
+    # a 12.5 % sample pays more additions per point than the full MSM: the scale factor stays below len/sample
+    k = full // 8
+    assert 1.0 < bench.cpu_scale(full, k, 16) < full / k
