@@ -1,0 +1,240 @@
+// g16_cli -- small driver over ark_groth16_b200.hpp: the compiled host side of the drop-in, used by the tests to run the
+// reference-shaped calls (CircomCircuit + ProvingKey bytes in, ark-serialize Proof bytes out) without Python in between.
+// It mirrors what `crescent prove` does around Groth16::prove (creds/src/lib.rs:255-303): read main_c.r1cs, read
+// prover_params.bin, take the witness, prove, write the proof -- nothing else of the CLI (no JWT handling, no show/verify).
+//
+//   g16_cli prove --r1cs F --pk F --witness F (--r HEX --s HEX | --seed N | --test-rng | --no-zk) [--reduction circom]
+//                 [--no-precompute] [--shards K] [--device D] [--repeat N] --out F
+//   g16_cli witness-map --r1cs F --witness F [--reduction circom] --out F      (n x 32 bytes, canonical little-endian)
+//   g16_cli rng (test | seed:N) COUNT          next_u64 draws of StdRng, one hex word per line
+//   g16_cli rand-fr (test | seed:N) COUNT      Fr::rand draws, canonical value as hex
+//   g16_cli r1cs F                              to_matrices(): "k row col coeff" lines
+//   g16_cli pk-roundtrip IN OUT                 deserialize_uncompressed_unchecked -> serialize_uncompressed
+//   g16_cli proof-ser AX AY BX0 BX1 BY0 BY1 CX CY    canonical coordinates ("inf" for a point: AX=inf AY=-)
+//   g16_cli fp (fr|fq) (from|into) HEX          host Montgomery marshalling check
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "ark_groth16_b200.hpp"
+
+using namespace ark_groth16_b200;
+
+static std::vector<uint8_t> read_file(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+static void write_file(const std::string& path, const std::vector<uint8_t>& b) {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot write " + path);
+    f.write(reinterpret_cast<const char*>(b.data()), (std::streamsize)b.size());
+}
+static std::string hex_bytes(const std::vector<uint8_t>& b) {
+    static const char* d = "0123456789abcdef";
+    std::string s;
+    for (uint8_t x : b) s.push_back(d[x >> 4]), s.push_back(d[x & 15]);
+    return s;
+}
+static StdRng make_rng(const std::string& spec) {
+    if (spec == "test") return test_rng();
+    if (spec.rfind("seed:", 0) == 0) return StdRng::seed_from_u64(std::stoull(spec.substr(5), nullptr, 0));
+    throw std::invalid_argument("rng spec must be `test` or `seed:N`");
+}
+
+struct Args {
+    std::map<std::string, std::string> kv;
+    std::vector<std::string> pos;
+    bool has(const std::string& k) const { return kv.count(k) != 0; }
+    std::string get(const std::string& k, const std::string& dflt = "") const { return has(k) ? kv.at(k) : dflt; }
+    std::string req(const std::string& k) const {
+        if (!has(k)) throw std::invalid_argument("missing --" + k);
+        return kv.at(k);
+    }
+};
+static Args parse(int argc, char** argv, int from) {
+    static const char* flags[] = {"test-rng", "no-zk", "no-precompute"};
+    Args a;
+    for (int i = from; i < argc; i++) {
+        std::string s = argv[i];
+        if (s.rfind("--", 0) == 0) {
+            std::string k = s.substr(2);
+            bool is_flag = false;
+            for (auto f : flags) is_flag = is_flag || k == f;
+            if (is_flag) a.kv[k] = "1";
+            else if (i + 1 < argc) a.kv[k] = argv[++i];
+            else throw std::invalid_argument("missing value for " + s);
+        } else
+            a.pos.push_back(s);
+    }
+    return a;
+}
+
+static Fr fr_from_hex(const std::string& h) {
+    auto v = Fr::from_bigint(detail::from_hex(h));
+    if (!v) throw std::invalid_argument("scalar not below the Fr modulus");
+    return *v;
+}
+
+template <class QAP>
+static int run_prove(const Args& a) {
+    auto r1cs = std::make_shared<const R1CS>(R1CS::from_file(R1CSFile::read(read_file(a.req("r1cs")))));
+    ProvingKey pk = ProvingKey::deserialize_uncompressed_unchecked(read_file(a.req("pk")));
+    std::vector<uint8_t> wbytes = read_file(a.req("witness"));
+    if (wbytes.size() != r1cs->num_variables * 32) throw std::invalid_argument("witness file must hold num_wires x 32 bytes");
+    int device = std::stoi(a.get("device", "0"));
+    bool precompute = !a.has("no-precompute");
+    int repeat = std::stoi(a.get("repeat", "1"));
+    int shards = std::stoi(a.get("shards", "1"));
+
+    Fr r = Fr::zero(), s = Fr::zero();
+    if (a.has("seed") || a.has("test-rng")) {
+        StdRng rng = a.has("test-rng") ? test_rng() : StdRng::seed_from_u64(std::stoull(a.req("seed"), nullptr, 0));
+        r = Fr::rand(rng);  // prover.rs:151-152: r first, then s
+        s = Fr::rand(rng);
+    } else if (!a.has("no-zk")) {
+        r = fr_from_hex(a.req("r"));
+        s = fr_from_hex(a.req("s"));
+    }
+
+    Proof proof;
+    double ms = 0;
+    if (shards <= 1) {
+        Groth16<QAP> prover(device, precompute);
+        CircomCircuit circuit{r1cs, fr_from_canonical_bulk(prover.context(), wbytes.data(), r1cs->num_variables)};
+        for (int k = 0; k < repeat; k++) {
+            auto t0 = std::chrono::steady_clock::now();
+            Proof p = prover.create_proof_with_reduction(circuit, pk, r, s);
+            ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (k && !(p == proof)) throw std::runtime_error("proof changed between repeats");
+            proof = p;
+        }
+        fprintf(stderr, "g16_cli: %llu kernel launches, last prove %.3f ms (host clock)\n", (unsigned long long)prover.launch_count(), ms);
+    } else {
+        ConstraintMatrices m = r1cs->to_matrices();
+        std::vector<int> devices;
+        int ndev = g16_device_count();
+        for (int k = 0; k < shards; k++) devices.push_back(ndev > 0 ? (device + k) % ndev : device + k);
+        Context conv(device);
+        std::vector<Fr> z = fr_from_canonical_bulk(conv, wbytes.data(), r1cs->num_variables);
+        ShardedGroth16<QAP> prover(devices, pk, m, precompute);
+        for (int k = 0; k < repeat; k++) {
+            Proof p = prover.prove(r, s, z);
+            if (k && !(p == proof)) throw std::runtime_error("proof changed between repeats");
+            proof = p;
+        }
+    }
+    write_file(a.req("out"), proof.serialize_uncompressed());
+    std::cout << hex_bytes(proof.serialize_compressed()) << "\n";
+    return 0;
+}
+
+template <class QAP>
+static int run_witness_map(const Args& a) {
+    R1CS r1cs = R1CS::from_file(R1CSFile::read(read_file(a.req("r1cs"))));
+    ConstraintMatrices m = r1cs.to_matrices();
+    std::vector<uint8_t> wbytes = read_file(a.req("witness"));
+    if (wbytes.size() != r1cs.num_variables * 32) throw std::invalid_argument("witness file must hold num_wires x 32 bytes");
+    Groth16<QAP> prover(std::stoi(a.get("device", "0")), false);
+    std::vector<Fr> z = fr_from_canonical_bulk(prover.context(), wbytes.data(), r1cs.num_variables);
+    std::vector<Fr> h = prover.witness_map_from_matrices(m, m.num_instance_variables, m.num_constraints, z);
+    std::vector<uint64_t> canon(h.size() * 4);
+    Context& ctx = prover.context();
+    ctx.check(g16_field_op(ctx.get(), G16_FIELD_FR, G16_OP_FROM_MONT, reinterpret_cast<const uint64_t*>(h.data()), nullptr, canon.data(), h.size()),
+              "g16_field_op(from_mont)");
+    std::vector<uint8_t> out(canon.size() * 8);
+    std::memcpy(out.data(), canon.data(), out.size());
+    write_file(a.req("out"), out);
+    std::cout << h.size() << "\n";
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) {
+        fprintf(stderr, "usage: g16_cli (prove|witness-map|rng|rand-fr|r1cs|pk-roundtrip|proof-ser|fp) ...  (see g16_cli.cpp)\n");
+        return 64;
+    }
+    std::string cmd = argv[1];
+    try {
+        Args a = parse(argc, argv, 2);
+        if (cmd == "prove") return a.get("reduction", "libsnark") == "circom" ? run_prove<CircomReduction>(a) : run_prove<LibsnarkReduction>(a);
+        if (cmd == "witness-map")
+            return a.get("reduction", "libsnark") == "circom" ? run_witness_map<CircomReduction>(a) : run_witness_map<LibsnarkReduction>(a);
+        if (cmd == "rng" || cmd == "rand-fr") {
+            StdRng rng = make_rng(a.pos.at(0));
+            int count = std::stoi(a.pos.at(1));
+            for (int i = 0; i < count; i++) {
+                if (cmd == "rng") printf("%016llx\n", (unsigned long long)rng.next_u64());
+                else std::cout << detail::to_hex(Fr::rand(rng).into_bigint()) << "\n";
+            }
+            return 0;
+        }
+        if (cmd == "r1cs") {
+            R1CS r = R1CS::from_file(R1CSFile::read(read_file(a.pos.at(0))));
+            ConstraintMatrices m = r.to_matrices();
+            printf("num_instance %zu num_witness %zu num_constraints %zu nnz %zu %zu %zu\n", m.num_instance_variables, m.num_witness_variables,
+                   m.num_constraints, m.a_num_non_zero(), m.b_num_non_zero(), m.c_num_non_zero());
+            const Csr* mats[3] = {&m.a, &m.b, &m.c};
+            for (int k = 0; k < 3; k++)
+                for (size_t i = 0; i < m.num_constraints; i++)
+                    for (uint64_t e = mats[k]->row_ptr[i]; e < mats[k]->row_ptr[i + 1]; e++) {
+                        Limbs v = {mats[k]->val[4 * e], mats[k]->val[4 * e + 1], mats[k]->val[4 * e + 2], mats[k]->val[4 * e + 3]};
+                        printf("%d %zu %u %s\n", k, i, mats[k]->col[e], detail::to_hex(v).c_str());
+                    }
+            return 0;
+        }
+        if (cmd == "pk-roundtrip") {
+            ProvingKey pk = ProvingKey::deserialize_uncompressed_unchecked(read_file(a.pos.at(0)));
+            write_file(a.pos.at(1), pk.serialize_uncompressed());
+            printf("a %zu b_g1 %zu b_g2 %zu h %zu l %zu gamma_abc %zu\n", pk.a_query.size(), pk.b_g1_query.size(), pk.b_g2_query.size(),
+                   pk.h_query.size(), pk.l_query.size(), pk.vk.gamma_abc_g1.size());
+            return 0;
+        }
+        if (cmd == "proof-ser") {
+            auto fq = [&](size_t i) {
+                auto v = Fq::from_bigint(detail::from_hex(a.pos.at(i)));
+                if (!v) throw std::invalid_argument("coordinate not below the Fq modulus");
+                return *v;
+            };
+            Proof p;
+            if (a.pos.at(0) != "inf") p.a = G1Affine{fq(0), fq(1), false};
+            if (a.pos.at(2) != "inf") p.b = G2Affine{Fq2{fq(2), fq(3)}, Fq2{fq(4), fq(5)}, false};
+            if (a.pos.at(6) != "inf") p.c = G1Affine{fq(6), fq(7), false};
+            std::cout << hex_bytes(p.serialize_compressed()) << "\n" << hex_bytes(p.serialize_uncompressed()) << "\n";
+            return 0;
+        }
+        if (cmd == "fp") {
+            bool fr = a.pos.at(0) == "fr";
+            Limbs x = detail::from_hex(a.pos.at(2));
+            Limbs y;
+            if (a.pos.at(1) == "from") {
+                if (fr) {
+                    auto v = Fr::from_bigint(x);
+                    if (!v) throw std::invalid_argument("not reduced");
+                    y = v->v;
+                } else {
+                    auto v = Fq::from_bigint(x);
+                    if (!v) throw std::invalid_argument("not reduced");
+                    y = v->v;
+                }
+            } else
+                y = fr ? Fr{x}.into_bigint() : Fq{x}.into_bigint();
+            std::cout << detail::to_hex(y) << "\n";
+            return 0;
+        }
+        fprintf(stderr, "g16_cli: unknown command %s\n", cmd.c_str());
+        return 64;
+    } catch (const SynthesisError& e) {
+        fprintf(stderr, "g16_cli: SynthesisError::%s: %s\n", e.kind == SynthesisError::PolynomialDegreeTooLarge ? "PolynomialDegreeTooLarge" : "AssignmentMissing", e.what());
+        return 3;
+    } catch (const Panic& e) {
+        fprintf(stderr, "g16_cli: panic (code %d): %s\n", e.code, e.what());
+        return 100 + e.code;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "g16_cli: %s\n", e.what());
+        return 2;
+    }
+}
