@@ -451,7 +451,7 @@ def main():
         out = {
             "metric": METRIC, "value": args.steps / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u32x8 (BN254 Fr/Fq Montgomery, exact)",
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (BN254 Fr/Fq Montgomery, exact)",
             "data": "synthetic",
             "config": {"workload": f"{args.workload} ({args.witness} witness)", "constraints": inst.nc, "wires": inst.m,
                        "domain": inst.n, "nnz": nnz, "parallelism": f"msm-shard{world}" if world > 1 else "single",

@@ -1,0 +1,352 @@
+"""pairing.py -- TEST INFRASTRUCTURE ONLY (the checker for the "next" row f-4: Groth16 verification).
+
+CPU restatement, in plain big-integer Python, of the verifier of the reference and of the BN254 pairing it calls:
+
+  forks/groth16/src/verifier.rs:13-20   prepare_verifying_key      -> prepare_verifying_key
+  forks/groth16/src/verifier.rs:25-39   prepare_inputs             -> prepare_inputs
+  forks/groth16/src/verifier.rs:44-65   verify_proof_with_prepared_inputs -> verify_proof_with_prepared_inputs
+  forks/groth16/src/verifier.rs:69-76   verify_proof               -> verify_proof
+
+The pairing itself is third-party to the reference tree (ark-ec ^0.4.2 `models::bn`, ark-bn254 0.4.0; semver ranges in
+forks/groth16/Cargo.toml:18-24, no lockfile in the tree).  Its published algorithm is restated here:
+  * tower Fq2 = Fq[u]/(u^2+1), Fq6 = Fq2[v]/(v^3 - xi), Fq12 = Fq6[w]/(w^2 - v), xi = 9 + u   (ark-bn254 Fq6Config/Fq12Config)
+  * G2Prepared: the line coefficients of the optimal-ate loop over the signed digits of 6x+2 (ATE_LOOP_COUNT), R kept in
+    homogeneous projective coordinates (double_in_place / add_in_place), then the two Frobenius additions Q1 = pi(Q),
+    Q2 = -pi^2(Q)
+  * multi_miller_loop: f <- f^2, f <- f * line(P) per pair ("ell", D-type twist: mul_by_034)
+  * final_exponentiation: easy part (q^6-1)(q^2+1), hard part after Fuentes-Castaneda et al. ("Faster hashing to G2"):
+    the result is  f^(2x(6x^2+3x+1) * (q^4-q^2+1)/r)  -- a fixed power of the reduced Tate pairing; this module checks that
+    identity numerically (hard_part_exponent) so the restated addition chain is pinned to the published exponent.
+ASSUMPTION (cannot be checked against an arkworks binary in this container): the digit string ATE_LOOP_COUNT, the order of
+the line multiplications inside one step and the hard-part chain are as published in ark-ec 0.4 / ark-bn254 0.4.  None of
+them changes a verification verdict; they only fix the bytes of GT elements such as PreparedVerifyingKey.alpha_g1_beta_g2.
+
+Here Fq12 is handled as Fq2[w]/(w^6 - xi) (six Fq2 coefficients), deliberately NOT the tower the CUDA code uses
+(Karatsuba over Fq6): the two only share the mathematics.  to_tower / from_tower convert to ark-serialize's coefficient order.
+Nothing under crescent_credentials_b200/ may import this file.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import pyref as R
+
+Q = R.Q_MOD
+F2 = R.Fq2
+XI = (9, 1)
+BN_X = 4965661367192848881  # ark-bn254 Config::X, X_IS_NEGATIVE = false
+# ark-bn254 Config::ATE_LOOP_COUNT: signed digits of 6x+2, least significant first (65 entries)
+ATE_LOOP_COUNT = [
+    0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, -1, 0, 0, 0, 0, 1, 1, 1, 0, 0, -1, 0, 0, 1,
+    0, 0, 0, 0, 0, -1, 0, 0, 1, 1, 0, 0, -1, 0, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, 1, 1,
+]
+assert sum(d << i for i, d in enumerate(ATE_LOOP_COUNT)) == 6 * BN_X + 2
+# the curve order and the field characteristic in terms of x (BN parametrisation) -- pins X itself
+assert 36 * BN_X**4 + 36 * BN_X**3 + 24 * BN_X**2 + 6 * BN_X + 1 == Q
+assert 36 * BN_X**4 + 36 * BN_X**3 + 18 * BN_X**2 + 6 * BN_X + 1 == R.R_MOD
+
+
+def f2_pow(a, e: int):
+    r = F2.ONE
+    while e:
+        if e & 1:
+            r = F2.mul(r, a)
+        a = F2.mul(a, a)
+        e >>= 1
+    return r
+
+
+def f2_conj(a):
+    return (a[0], (-a[1]) % Q)
+
+
+# ---- Fq12 = Fq2[w]/(w^6 - xi): a list of six Fq2 coefficients ------------------------------------------------------------
+F12_ONE = [F2.ONE] + [F2.ZERO] * 5
+
+
+def f12_mul(a, b):
+    t = [F2.ZERO] * 11
+    for i in range(6):
+        if a[i] == F2.ZERO:
+            continue
+        for j in range(6):
+            t[i + j] = F2.add(t[i + j], F2.mul(a[i], b[j]))
+    return [F2.add(t[k], F2.mul(XI, t[k + 6])) if k < 5 else t[k] for k in range(6)]
+
+
+def f12_sqr(a):
+    return f12_mul(a, a)
+
+
+def f12_conj(a):
+    """x -> x^(q^6): w -> -w (cyclotomic_inverse_in_place on the cyclotomic subgroup)."""
+    return [a[k] if k % 2 == 0 else F2.neg(a[k]) for k in range(6)]
+
+
+# w^(q^n) = w * xi^((q^n - 1)/6)
+_FROB = {n: [f2_pow(XI, k * (Q**n - 1) // 6) for k in range(6)] for n in (1, 2, 3)}
+
+
+def f12_frobenius(a, n: int):
+    out = []
+    for k in range(6):
+        c = f2_conj(a[k]) if n % 2 else a[k]
+        out.append(F2.mul(c, _FROB[n][k]))
+    return out
+
+
+def f12_pow(a, e: int):
+    r = list(F12_ONE)
+    for bit in bin(e)[2:]:
+        r = f12_sqr(r)
+        if bit == "1":
+            r = f12_mul(r, a)
+    return r
+
+
+def f12_inv(a):
+    """Inverse through the norm to Fq6 = Fq2[v]/(v^3 - xi), v = w^2: a = A(v) + w B(v); 1/a = (A - wB)/(A^2 - v B^2)."""
+    A = [a[0], a[2], a[4]]
+    B = [a[1], a[3], a[5]]
+    n = f6_sub(f6_mul(A, A), f6_mul_by_v(f6_mul(B, B)))
+    ni = f6_inv(n)
+    A2 = f6_mul(A, ni)
+    B2 = f6_mul(B, ni)
+    return [A2[0], F2.neg(B2[0]), A2[1], F2.neg(B2[1]), A2[2], F2.neg(B2[2])]
+
+
+def f6_mul(a, b):
+    t = [F2.ZERO] * 5
+    for i in range(3):
+        for j in range(3):
+            t[i + j] = F2.add(t[i + j], F2.mul(a[i], b[j]))
+    return [F2.add(t[0], F2.mul(XI, t[3])), F2.add(t[1], F2.mul(XI, t[4])), t[2]]
+
+
+def f6_sub(a, b):
+    return [F2.sub(x, y) for x, y in zip(a, b)]
+
+
+def f6_mul_by_v(a):
+    return [F2.mul(XI, a[2]), a[0], a[1]]
+
+
+def f6_inv(a):
+    c0, c1, c2 = a
+    t0 = F2.sub(F2.sqr(c0), F2.mul(XI, F2.mul(c1, c2)))
+    t1 = F2.sub(F2.mul(XI, F2.sqr(c2)), F2.mul(c0, c1))
+    t2 = F2.sub(F2.sqr(c1), F2.mul(c0, c2))
+    d = F2.add(F2.mul(c0, t0), F2.mul(XI, F2.add(F2.mul(c2, t1), F2.mul(c1, t2))))
+    di = F2.inv(d)
+    return [F2.mul(t0, di), F2.mul(t1, di), F2.mul(t2, di)]
+
+
+def to_tower(a) -> List[int]:
+    """ark-serialize order of an Fq12: c0.(c0,c1,c2) then c1.(c0,c1,c2), each Fq2 as (c0, c1): 12 Fq integers.
+    Tower coefficient (i, j) of v^i w^j is the w-power 2i + j."""
+    out = []
+    for j in (0, 1):
+        for i in range(3):
+            out += [a[2 * i + j][0], a[2 * i + j][1]]
+    return out
+
+
+def from_tower(t: Sequence[int]):
+    a = [None] * 6
+    k = 0
+    for j in (0, 1):
+        for i in range(3):
+            a[2 * i + j] = (t[k] % Q, t[k + 1] % Q)
+            k += 2
+    return a
+
+
+# ---- G2Prepared (ark-ec models/bn/g2.rs) ---------------------------------------------------------------------------------
+TWIST_MUL_BY_Q_X = f2_pow(XI, (Q - 1) // 3)
+TWIST_MUL_BY_Q_Y = f2_pow(XI, (Q - 1) // 2)
+TWO_INV = R.inv_mod(2, Q)
+
+
+def mul_by_char(P):
+    x, y = P
+    return (F2.mul(f2_conj(x), TWIST_MUL_BY_Q_X), F2.mul(f2_conj(y), TWIST_MUL_BY_Q_Y))
+
+
+def _double_in_place(r):
+    x, y, z = r
+    a = F2.scal(F2.mul(x, y), TWO_INV)
+    b = F2.sqr(y)
+    c = F2.sqr(z)
+    e = F2.mul(R.G2_B, F2.add(F2.add(c, c), c))
+    f = F2.add(F2.add(e, e), e)
+    g = F2.scal(F2.add(b, f), TWO_INV)
+    h = F2.sub(F2.sqr(F2.add(y, z)), F2.add(b, c))
+    i = F2.sub(e, b)
+    j = F2.sqr(x)
+    e2 = F2.sqr(e)
+    r[0] = F2.mul(a, F2.sub(b, f))
+    r[1] = F2.sub(F2.sqr(g), F2.add(F2.add(e2, e2), e2))
+    r[2] = F2.mul(b, h)
+    return (F2.neg(h), F2.add(F2.add(j, j), j), i)  # TwistType::D
+
+
+def _add_in_place(r, q):
+    x, y, z = r
+    theta = F2.sub(y, F2.mul(q[1], z))
+    lam = F2.sub(x, F2.mul(q[0], z))
+    c = F2.sqr(theta)
+    d = F2.sqr(lam)
+    e = F2.mul(lam, d)
+    f = F2.mul(z, c)
+    g = F2.mul(x, d)
+    h = F2.sub(F2.add(e, f), F2.add(g, g))
+    r[0] = F2.mul(lam, h)
+    r[1] = F2.sub(F2.mul(theta, F2.sub(g, h)), F2.mul(e, y))
+    r[2] = F2.mul(z, e)
+    j = F2.sub(F2.mul(theta, q[0]), F2.mul(lam, q[1]))
+    return (lam, F2.neg(theta), j)  # TwistType::D
+
+
+def g2_prepare(Qp) -> Optional[List[Tuple]]:
+    """G2Prepared::from: the list of line coefficients (None for the point at infinity)."""
+    if Qp is None:
+        return None
+    r = [Qp[0], Qp[1], F2.ONE]
+    negq = (Qp[0], F2.neg(Qp[1]))
+    coeffs = []
+    for bit in reversed(ATE_LOOP_COUNT[:-1]):
+        coeffs.append(_double_in_place(r))
+        if bit == 1:
+            coeffs.append(_add_in_place(r, Qp))
+        elif bit == -1:
+            coeffs.append(_add_in_place(r, negq))
+    q1 = mul_by_char(Qp)
+    q2 = mul_by_char(q1)
+    q2 = (q2[0], F2.neg(q2[1]))
+    coeffs.append(_add_in_place(r, q1))
+    coeffs.append(_add_in_place(r, q2))
+    return coeffs
+
+
+def _ell(f, coeff, P):
+    """f * (c0*P.y + c1*P.x * w + c2 * v w)  -- mul_by_034 on the tower = w-powers 0, 1, 3."""
+    c0 = F2.scal(coeff[0], P[1])
+    c1 = F2.scal(coeff[1], P[0])
+    line = [c0, c1, F2.ZERO, coeff[2], F2.ZERO, F2.ZERO]
+    return f12_mul(f, line)
+
+
+def multi_miller_loop(ps: Sequence, qs: Sequence):
+    """Bn::multi_miller_loop over pairs (G1 affine or None, G2 affine or None); pairs with an infinity are skipped."""
+    pairs = [(p, iter(g2_prepare(q))) for p, q in zip(ps, qs) if p is not None and q is not None]
+    f = list(F12_ONE)
+    n = len(ATE_LOOP_COUNT)
+    for i in range(n - 1, 0, -1):
+        if i != n - 1:
+            f = f12_sqr(f)
+        for p, it in pairs:
+            f = _ell(f, next(it), p)
+        bit = ATE_LOOP_COUNT[i - 1]
+        if bit in (1, -1):
+            for p, it in pairs:
+                f = _ell(f, next(it), p)
+    for p, it in pairs:
+        f = _ell(f, next(it), p)
+    for p, it in pairs:
+        f = _ell(f, next(it), p)
+    return f
+
+
+def _exp_by_neg_x(f):
+    return f12_conj(f12_pow(f, BN_X))
+
+
+def final_exponentiation(f):
+    """Bn::final_exponentiation; None when f is not invertible (f == 0)."""
+    if all(c == F2.ZERO for c in f):
+        return None
+    f1 = f12_conj(f)
+    f2 = f12_inv(f)
+    r = f12_mul(f1, f2)
+    f2 = r
+    r = f12_mul(f12_frobenius(r, 2), f2)
+    return hard_part(r)
+
+
+def hard_part(r):
+    y0 = _exp_by_neg_x(r)
+    y1 = f12_sqr(y0)
+    y2 = f12_sqr(y1)
+    y3 = f12_mul(y2, y1)
+    y4 = _exp_by_neg_x(y3)
+    y5 = f12_sqr(y4)
+    y6 = _exp_by_neg_x(y5)
+    y3 = f12_conj(y3)
+    y6 = f12_conj(y6)
+    y7 = f12_mul(y6, y4)
+    y8 = f12_mul(y7, y3)
+    y9 = f12_mul(y8, y1)
+    y10 = f12_mul(y8, y4)
+    y11 = f12_mul(y10, r)
+    y12 = f12_frobenius(y9, 1)
+    y13 = f12_mul(y12, y11)
+    y8 = f12_frobenius(y8, 2)
+    y14 = f12_mul(y8, y13)
+    rc = f12_conj(r)
+    y15 = f12_frobenius(f12_mul(rc, y9), 3)
+    return f12_mul(y15, y14)
+
+
+def hard_part_exponent() -> int:
+    """2x(6x^2+3x+1) * (q^4 - q^2 + 1)/r, the exponent ark-ec's comment states for the hard part."""
+    x = BN_X
+    return 2 * x * (6 * x * x + 3 * x + 1) * ((Q**4 - Q**2 + 1) // R.R_MOD)
+
+
+def pairing(P, Qp):
+    """E::pairing(P, Q).0"""
+    return final_exponentiation(multi_miller_loop([P], [Qp]))
+
+
+# ---- the verifier (forks/groth16/src/verifier.rs) --------------------------------------------------------------------------
+class PreparedVerifyingKey:
+    def __init__(self, vk, alpha_g1_beta_g2, gamma_g2_neg, delta_g2_neg):
+        self.vk = vk
+        self.alpha_g1_beta_g2 = alpha_g1_beta_g2
+        self.gamma_g2_neg = gamma_g2_neg
+        self.delta_g2_neg = delta_g2_neg
+
+
+def prepare_verifying_key(vk) -> PreparedVerifyingKey:
+    """verifier.rs:13-20"""
+    return PreparedVerifyingKey(vk, pairing(vk.alpha_g1, vk.beta_g2), R.G2.neg(vk.gamma_g2), R.G2.neg(vk.delta_g2))
+
+
+class MalformedVerifyingKey(Exception):
+    """SynthesisError::MalformedVerifyingKey (verifier.rs:29-31)"""
+
+
+def prepare_inputs(pvk: PreparedVerifyingKey, public_inputs: Sequence[int]):
+    """verifier.rs:25-39: gamma_abc_g1[0] + sum x_i * gamma_abc_g1[i+1] (Jacobian result)."""
+    abc = pvk.vk.gamma_abc_g1
+    if len(public_inputs) + 1 != len(abc):
+        raise MalformedVerifyingKey()
+    acc = R.G1.to_jac(abc[0])
+    for x, b in zip(public_inputs, abc[1:]):
+        acc = R.G1.jadd(acc, R.G1.jmul(R.G1.to_jac(b), x % R.R_MOD))
+    return acc
+
+
+def verify_proof_with_prepared_inputs(pvk: PreparedVerifyingKey, proof, prepared_inputs_jac) -> bool:
+    """verifier.rs:44-65.  proof = (A, B, C) affine (None = infinity)."""
+    A, B, C = proof
+    f = multi_miller_loop([A, R.G1.to_affine(prepared_inputs_jac), C], [B, pvk.gamma_g2_neg, pvk.delta_g2_neg])
+    t = final_exponentiation(f)
+    if t is None:
+        raise ValueError("UnexpectedIdentity")
+    return t == pvk.alpha_g1_beta_g2
+
+
+def verify_proof(pvk: PreparedVerifyingKey, proof, public_inputs: Sequence[int]) -> bool:
+    """verifier.rs:69-76"""
+    return verify_proof_with_prepared_inputs(pvk, proof, prepare_inputs(pvk, public_inputs))
