@@ -135,6 +135,7 @@ void g16_ctx_destroy(g16_ctx* ctx) {
         dev_free(kv.second.odd_scaled);
         dev_free(kv.second.coset_inv_z);
     }
+    verify_free(ctx);
     dev_free(ctx->d_small);
     dev_free(ctx->d_partial);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -1002,6 +1003,7 @@ int g16_set_option(g16_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "spmv_sell")) ctx->opt_spmv_sell = value;
     else if (!strcmp(key, "wm_priority")) ctx->opt_wm_priority = value;
     else if (!strcmp(key, "ba_prefetch")) ctx->opt_ba_prefetch = value;
+    else if (!strcmp(key, "verify_occupancy")) ctx->opt_verify_occupancy = value;
     else return set_err(ctx, G16_ERR_BAD_ARG, "unknown option '%s'", key);
     return G16_OK;
 }

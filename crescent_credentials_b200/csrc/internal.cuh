@@ -94,6 +94,25 @@ struct CsrDev {
 };
 constexpr uint32_t kSellNoRow = 0xFFFFFFFFu;
 
+// ---- verifier state (verify.cu): the PreparedVerifyingKey of forks/groth16/src/data_structures.rs:62-72 on the device -----
+struct VerifyKeyDev {
+    bool have = false;
+    size_t n_inputs = 0;           // gamma_abc_g1.len() - 1
+    G1Affine* abc0 = nullptr;      // device: gamma_abc_g1[0]
+    G1Affine* abc_tbl = nullptr;   // device: window tables of gamma_abc_g1[1..] (pairing.cuh: prepare_inputs_one)
+    void* neg_gamma = nullptr;     // device: EllCoeff[kEllCoeffs] of -gamma_g2 (gamma_g2_neg_pc)
+    void* neg_delta = nullptr;     // device: EllCoeff[kEllCoeffs] of -delta_g2 (delta_g2_neg_pc)
+    void* alpha_beta = nullptr;    // device: Fq12 e(alpha_g1, beta_g2)
+    uint64_t alpha_beta_host[48] = {};
+    unsigned g2_inf = 0;           // bit 1 / 2: gamma_g2 / delta_g2 is the point at infinity (pair filtered out, as the reference does)
+    // per-call scratch, grown on demand
+    void* proofs = nullptr;        // g16_proof[cap]
+    Fr* inputs = nullptr;          // [cap * n_inputs]
+    G1Affine* prepared = nullptr;  // [cap]
+    uint8_t* verdict = nullptr;    // [cap]
+    size_t cap = 0;
+};
+
 }  // namespace g16
 
 struct g16_ctx {
@@ -159,6 +178,9 @@ struct g16_ctx {
     cudaEvent_t ev_acc[10] = {};
     bool pre_pending = false;  // k_assemble_pre already in flight for (pre_r, pre_s)
     uint64_t pre_r[4] = {}, pre_s[4] = {};
+
+    g16::VerifyKeyDev vk;  // row f-4
+    int opt_verify_occupancy = 8;  // resident warps per SM k_verify is compiled for (8 / 12 / 16)
 
     // generic MSM slots
     g16::MsmBases slot[g16::kMsmSlots];
@@ -249,5 +271,8 @@ G2Affine g2_generator();
 int scale_point_dev(g16_ctx* ctx, const void* in_xyzz, const uint64_t* k_mont, void* out_xyzz, cudaStream_t st);
 int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, g16_proof* out, cudaStream_t st);
 int xyzz_to_affine_host(g16_ctx* ctx, int group, const void* xyzz_dev, uint64_t* out, int* out_inf, cudaStream_t st);
+
+// verify.cu ---------------------------------------------------------------------------------------------------------------
+void verify_free(g16_ctx* ctx);
 
 }  // namespace g16

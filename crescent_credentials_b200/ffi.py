@@ -30,7 +30,10 @@ EXPORTS = [
     "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count", "g16_set_option",
     "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare", "g16_get_msm_stats", "g16_ctx_load_pk_ranges",
     "g16_prove_shard_begin_dev", "g16_prove_shard_finish_dev", "g16_copy_h_dev",
+    "g16_ctx_load_vk", "g16_vk_alpha_beta", "g16_prepare_inputs", "g16_verify_batch", "g16_verify_batch_prepared",
+    "g16_verify_batch_dev", "g16_pairing",
 ]
+VERDICT_REJECT, VERDICT_ACCEPT, VERDICT_UNEXPECTED_IDENTITY = 0, 1, 2
 
 _u64p = C.POINTER(C.c_uint64)
 _u32p = C.POINTER(C.c_uint32)
@@ -53,6 +56,11 @@ class R1csView(C.Structure):
         ("num_constraints", C.c_uint64), ("num_instance", C.c_uint64), ("num_wires", C.c_uint64),
         ("row_ptr", _u64p * 3), ("col", _u32p * 3), ("val", _u64p * 3), ("encoding", C.c_int),
     ]
+
+
+class VkView(C.Structure):
+    _fields_ = [("alpha_g1", _u64p), ("beta_g2", _u64p), ("gamma_g2", _u64p), ("delta_g2", _u64p),
+                ("gamma_abc_g1", _u64p), ("gamma_abc_len", C.c_size_t), ("encoding", C.c_int)]
 
 
 class ProofOut(C.Structure):
@@ -147,6 +155,13 @@ def load_library() -> C.CDLL:
     lib.g16_bench_int_pipe.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     lib.g16_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.g16_pow_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.g16_ctx_load_vk.argtypes = [C.c_void_p, C.POINTER(VkView)]
+    lib.g16_vk_alpha_beta.argtypes = [C.c_void_p, C.c_void_p]
+    lib.g16_prepare_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.g16_verify_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.g16_verify_batch_prepared.argtypes = lib.g16_verify_batch.argtypes
+    lib.g16_verify_batch_dev.argtypes = lib.g16_verify_batch.argtypes
+    lib.g16_pairing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     _lib = lib
     return lib
 
@@ -411,6 +426,56 @@ class Context:
         s = np.ascontiguousarray(s, dtype=np.uint64)
         out = ProofOut()
         self.check(self.lib.g16_prove_combine_dev(self.h, C.c_void_p(dev_partials), count, _ptr(r), _ptr(s), C.byref(out)))
+        return out
+
+    # ---- verification (row f-4) -------------------------------------------------------------------------------------------
+    def load_vk(self, alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1, encoding=ENC_MONTGOMERY):
+        """prepare_verifying_key on the device.  Arrays of uint64 limbs: 8 / 16 / 16 / 16 words and (len, 8)."""
+        keep = [np.ascontiguousarray(a, dtype=np.uint64) for a in (alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1)]
+        abc = keep[4].reshape(-1, 8)
+        v = VkView()
+        v.alpha_g1, v.beta_g2, v.gamma_g2, v.delta_g2 = (k.ctypes.data_as(_u64p) for k in keep[:4])
+        v.gamma_abc_g1 = abc.ctypes.data_as(_u64p)
+        v.gamma_abc_len = abc.shape[0]
+        v.encoding = encoding
+        self.check(self.lib.g16_ctx_load_vk(self.h, C.byref(v)))
+        self.vk_inputs = abc.shape[0] - 1
+
+    def vk_alpha_beta(self) -> np.ndarray:
+        out = np.zeros(48, dtype=np.uint64)
+        self.check(self.lib.g16_vk_alpha_beta(self.h, _ptr(out)))
+        return out
+
+    def prepare_inputs(self, public_inputs: np.ndarray, n: int) -> np.ndarray:
+        x = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+        out = np.zeros((n, 8), dtype=np.uint64)
+        self.check(self.lib.g16_prepare_inputs(self.h, _ptr(x) if x.size else None, n, _ptr(out)))
+        return out
+
+    def verify_batch(self, proofs, public_inputs: np.ndarray, n: int) -> np.ndarray:
+        """proofs: ctypes array of ProofOut (g16_proof) or a uint8 numpy buffer of n * 272 bytes."""
+        x = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+        out = np.zeros(n, dtype=np.uint8)
+        pp = _ptr(proofs) if isinstance(proofs, np.ndarray) else C.cast(proofs, C.c_void_p)
+        self.check(self.lib.g16_verify_batch(self.h, pp, _ptr(x) if x.size else None, n, _ptr(out)))
+        return out
+
+    def verify_batch_prepared(self, proofs, prepared: np.ndarray, n: int) -> np.ndarray:
+        x = np.ascontiguousarray(prepared, dtype=np.uint64)
+        out = np.zeros(n, dtype=np.uint8)
+        pp = _ptr(proofs) if isinstance(proofs, np.ndarray) else C.cast(proofs, C.c_void_p)
+        self.check(self.lib.g16_verify_batch_prepared(self.h, pp, _ptr(x), n, _ptr(out)))
+        return out
+
+    def verify_batch_dev(self, proofs_dev: int, inputs_dev: int, n: int, verdict_dev: int):
+        self.check(self.lib.g16_verify_batch_dev(self.h, _ptr(proofs_dev), _ptr(inputs_dev) if inputs_dev else None, n, _ptr(verdict_dev)))
+
+    def pairing(self, g1_points: np.ndarray, g2_points: np.ndarray) -> np.ndarray:
+        p = np.ascontiguousarray(g1_points, dtype=np.uint64).reshape(-1, 8)
+        q = np.ascontiguousarray(g2_points, dtype=np.uint64).reshape(-1, 16)
+        assert p.shape[0] == q.shape[0]
+        out = np.zeros((p.shape[0], 48), dtype=np.uint64)
+        self.check(self.lib.g16_pairing(self.h, _ptr(p), _ptr(q), p.shape[0], _ptr(out)))
         return out
 
     def timings(self) -> dict:

@@ -12,6 +12,10 @@
  *   ark-poly EvaluationDomain::{fft,ifft}_in_place (+ coset) call sites r1cs_to_qap.rs:179-210 -> g16_ntt
  *   ark-ff Fp mul/add/sub/inverse (K1 parity hook)                                            -> g16_field_op
  *   forks/groth16/src/generator.rs:133-194 FixedBase::msm (key minting, "next" row f-2)       -> g16_fixed_base_g1 / _g2
+ *   forks/groth16/src/verifier.rs:13-20   prepare_verifying_key ("next" row f-4)              -> g16_ctx_load_vk, g16_vk_alpha_beta
+ *   forks/groth16/src/verifier.rs:25-39   Groth16::prepare_inputs                             -> g16_prepare_inputs
+ *   forks/groth16/src/verifier.rs:44-76   verify_proof[_with_prepared_inputs], one call per proof -> g16_verify_batch (n proofs per call)
+ *   ark-ec Pairing::pairing / multi_miller_loop + final_exponentiation call sites verifier.rs:17,48-62 -> g16_pairing
  *
  * Data layout at the boundary (all host pointers unless a function says "dev"):
  *   Fr / Fq element : 4 x uint64 little-endian limbs in Montgomery form (R = 2^256) -- byte-identical to arkworks'
@@ -191,7 +195,8 @@ int g16_get_timings(g16_ctx* ctx, g16_timings* out);
  * "wm_priority" = 1 runs the witness map and the h MSM on a high-priority stream (default 0),
  * "ntt_radix4" = 0 / 1 forces the radix-2 / radix-4 transform passes (default -1: radix-4 only when no MSM runs beside),
  * "spmv_sell" = 0 selects the row-per-thread CSR kernel instead of the sliced-ELL one (default 1),
- * "ba_prefetch" = 1 / 2 selects the cp.async / L2-prefetch variants of k_ba_add (default 0; both measured slower).
+ * "ba_prefetch" = 1 / 2 selects the cp.async / L2-prefetch variants of k_ba_add (default 0; both measured slower),
+ * "verify_occupancy" = 8 / 12 / 16 selects the k_verify build for that many resident warps per SM (255 / 168 / 128 registers).
  * No option changes a result bit.  Unknown keys return G16_ERR_BAD_ARG. */
 int g16_set_option(g16_ctx* ctx, const char* key, int value);
 
@@ -227,6 +232,44 @@ int g16_pow_table(g16_ctx* ctx, const uint64_t base[4], const uint64_t scale[4],
 /* Sparse R1CS evaluation a = A z, b = B z, c = C z over the loaded matrices (evaluate_constraint,
  * r1cs_to_qap.rs:16-45); outputs nc Montgomery elements each (any may be NULL). */
 int g16_r1cs_eval(g16_ctx* ctx, const uint64_t* z, uint64_t* az, uint64_t* bz, uint64_t* cz);
+
+/* ---- verification ("next" row f-4; forks/groth16/src/verifier.rs) --------------------------------------------------- */
+/* VerifyingKey view (data_structures.rs:31-44; delta_g1 is not read by the verifier).  gamma_abc_g1: gamma_abc_len G1 points,
+ * entry 0 pairs with the constant-1 wire. */
+typedef struct g16_vk_view {
+    const uint64_t* alpha_g1;     /* G1 */
+    const uint64_t* beta_g2;      /* G2 */
+    const uint64_t* gamma_g2;     /* G2 */
+    const uint64_t* delta_g2;     /* G2 */
+    const uint64_t* gamma_abc_g1; size_t gamma_abc_len;
+    int encoding;                 /* G16_ENC_* of every coordinate above */
+} g16_vk_view;
+
+#define G16_VERDICT_REJECT 0
+#define G16_VERDICT_ACCEPT 1
+#define G16_VERDICT_UNEXPECTED_IDENTITY 2 /* final_exponentiation returned None (SynthesisError::UnexpectedIdentity, verifier.rs:62) */
+
+/* prepare_verifying_key (verifier.rs:13-20): uploads the key and computes on the device e(alpha_g1, beta_g2), the line
+ * coefficients of -gamma_g2 and -delta_g2 (G2Prepared) and fixed-base window tables of gamma_abc_g1[1..]. */
+int g16_ctx_load_vk(g16_ctx* ctx, const g16_vk_view* vk);
+/* PreparedVerifyingKey.alpha_g1_beta_g2: an Fq12 as 12 Montgomery Fq in ark-serialize order (c0.c0.c0 ... c1.c2.c1). */
+int g16_vk_alpha_beta(g16_ctx* ctx, uint64_t out[48]);
+/* prepare_inputs (verifier.rs:25-39) for n instances: public_inputs holds n * (gamma_abc_len - 1) Montgomery Fr, instance-major
+ * (the constant-1 wire is NOT passed, as in the reference); out receives n affine G1 points (Montgomery, infinity = (0, 0)). */
+int g16_prepare_inputs(g16_ctx* ctx, const uint64_t* public_inputs, size_t n, uint64_t* out_points);
+/* verify_proof (verifier.rs:69-76) for n (proof, instance) pairs under the loaded key, one device thread per proof:
+ * verdict[i] = G16_VERDICT_* of pair i -- exactly the reference's verdict for that pair (no random linear combination across
+ * proofs, so one bad proof cannot hide and none can be blamed wrongly).  As in the reference, points are not checked for
+ * curve or subgroup membership. */
+int g16_verify_batch(g16_ctx* ctx, const g16_proof* proofs, const uint64_t* public_inputs, size_t n, uint8_t* verdict);
+/* verify_proof_with_prepared_inputs (verifier.rs:44-65): as g16_verify_batch, with the n prepared-input points (affine G1,
+ * Montgomery, 8 x u64 each, (0, 0) = infinity) supplied by the caller instead of the public inputs. */
+int g16_verify_batch_prepared(g16_ctx* ctx, const g16_proof* proofs, const uint64_t* prepared_inputs, size_t n, uint8_t* verdict);
+/* Same with everything resident on the device (g16_proof[n], Fr[n * (gamma_abc_len - 1)], uint8_t[n]); stream-ordered. */
+int g16_verify_batch_dev(g16_ctx* ctx, const void* proofs_dev, const void* public_inputs_dev, size_t n, void* verdict_dev);
+/* E::pairing(p_i, q_i).0 for n pairs (parity hook): gt_out receives n Fq12 (48 x u64 each, layout as g16_vk_alpha_beta).
+ * A pair holding a point at infinity yields one. */
+int g16_pairing(g16_ctx* ctx, const uint64_t* g1_points, const uint64_t* g2_points, size_t n, uint64_t* gt_out);
 
 /* ---- device memory + micro-benchmarks ------------------------------------------------------------------------------ */
 int g16_dev_alloc(g16_ctx* ctx, size_t bytes, void** dev_ptr);

@@ -1,0 +1,263 @@
+"""CPU tests for row f-4 (Groth16 verification): the big-integer pairing oracle is pinned to the algebra (bilinearity, the
+published hard-part exponent, Frobenius = q-th power) and to the golden proofs (every committed proof satisfies the real
+pairing equation of forks/groth16/src/verifier.rs:44-65); the DEVICE pairing code (csrc/pairing.cuh, compiled for the host
+with the carry chains emulated in C) is then compared with that oracle value by value."""
+import ctypes
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import pairing as P
+import pyref as o
+from conftest import GOLDEN, GOLDEN_NAMES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+Q = o.Q_MOD
+
+
+# ---- encoding helpers: Montgomery 8 x u32 limbs ---------------------------------------------------------------------------
+def enc_fq(vals):
+    return b"".join(o.mont_le_bytes(v % Q, Q) for v in vals)
+
+
+def dec_fq(buf):
+    return [o.from_mont(int.from_bytes(buf[i:i + 32], "little"), Q) for i in range(0, len(buf), 32)]
+
+
+def enc_f12(a):
+    return enc_fq(P.to_tower(a))
+
+
+def dec_f12(buf):
+    return P.from_tower(dec_fq(buf))
+
+
+def enc_g1(p):
+    return enc_fq([0, 0] if p is None else [p[0], p[1]])
+
+
+def enc_g2(p):
+    return enc_fq([0, 0, 0, 0] if p is None else [p[0][0], p[0][1], p[1][0], p[1][1]])
+
+
+def enc_coeffs(cs):
+    return b"".join(enc_fq([c[0][0], c[0][1], c[1][0], c[1][1], c[2][0], c[2][1]]) for c in cs)
+
+
+def rand_f12(rng):
+    return [(rng.randrange(Q), rng.randrange(Q)) for _ in range(6)]
+
+
+def load_vk_and_proof(name):
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        meta = json.load(f)
+    with open(os.path.join(GOLDEN, name + ".pk.bin"), "rb") as f:
+        buf = f.read()
+    vk = o.VerifyingKey()
+    p = 0
+    vk.alpha_g1 = o.deser_g1_uncompressed(buf[p:p + 64]); p += 64
+    vk.beta_g2 = o.deser_g2_uncompressed(buf[p:p + 128]); p += 128
+    vk.gamma_g2 = o.deser_g2_uncompressed(buf[p:p + 128]); p += 128
+    vk.delta_g1 = o.deser_g1_uncompressed(buf[p:p + 64]); p += 64
+    vk.delta_g2 = o.deser_g2_uncompressed(buf[p:p + 128]); p += 128
+    n = int.from_bytes(buf[p:p + 8], "little"); p += 8
+    vk.gamma_abc_g1 = [o.deser_g1_uncompressed(buf[p + 64 * i:p + 64 * i + 64]) for i in range(n)]
+    pb = bytes.fromhex(meta["proof_uncompressed"])
+    proof = (o.deser_g1_uncompressed(pb[:64]), o.deser_g2_uncompressed(pb[64:192]), o.deser_g1_uncompressed(pb[192:]))
+    ni = int(meta["num_instance"])
+    z = [int(v, 16) for v in meta["z"]]
+    return vk, proof, z[1:ni]
+
+
+# ---- the oracle itself ---------------------------------------------------------------------------------------------------------
+def test_oracle_pairing_is_bilinear_nondegenerate_and_of_order_r():
+    e = P.pairing(o.G1_GEN, o.G2_GEN)
+    assert e != P.F12_ONE
+    assert P.f12_pow(e, o.R_MOD) == P.F12_ONE
+    a, b = o.stream_fr(0x9A1, 1), o.stream_fr(0x9A1, 2)
+    assert P.pairing(o.G1.mul(o.G1_GEN, a), o.G2.mul(o.G2_GEN, b)) == P.f12_pow(e, a * b % o.R_MOD)
+    assert P.pairing(None, o.G2_GEN) == P.F12_ONE and P.pairing(o.G1_GEN, None) == P.F12_ONE
+    m = P.multi_miller_loop([o.G1_GEN, o.G1.neg(o.G1_GEN)], [o.G2_GEN, o.G2_GEN])
+    assert P.final_exponentiation(m) == P.F12_ONE
+
+
+def test_oracle_hard_part_chain_equals_the_published_exponent():
+    """ark-ec's comment: result = elt^(2z(6z^2+3z+1)(q^4-q^2+1)/r).  The restated addition chain must be that power."""
+    f = P.multi_miller_loop([o.G1_GEN], [o.G2_GEN])
+    r = P.f12_mul(P.f12_conj(f), P.f12_inv(f))
+    r = P.f12_mul(P.f12_frobenius(r, 2), r)
+    assert P.hard_part(r) == P.f12_pow(r, P.hard_part_exponent())
+
+
+def test_oracle_frobenius_is_the_q_power_and_inverse_inverts():
+    rng = random.Random(5)
+    x = rand_f12(rng)
+    assert P.f12_frobenius(x, 1) == P.f12_pow(x, Q)
+    assert P.f12_frobenius(P.f12_frobenius(x, 1), 1) == P.f12_frobenius(x, 2)
+    assert P.f12_frobenius(P.f12_frobenius(x, 2), 1) == P.f12_frobenius(x, 3)
+    assert P.f12_mul(x, P.f12_inv(x)) == P.F12_ONE
+    assert P.from_tower(P.to_tower(x)) == x
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_golden_proofs_satisfy_the_pairing_equation(name):
+    """verifier.rs:44-65 on every committed proof: accepted; a changed public input, a changed C and swapped A/C: rejected."""
+    vk, proof, inputs = load_vk_and_proof(name)
+    pvk = P.prepare_verifying_key(vk)
+    assert P.verify_proof(pvk, proof, inputs)
+    if inputs:
+        assert not P.verify_proof(pvk, proof, [(inputs[0] + 1) % o.R_MOD] + inputs[1:])
+    assert not P.verify_proof(pvk, (proof[0], proof[1], o.G1.add(proof[2], o.G1_GEN)), inputs)
+    assert not P.verify_proof(pvk, (proof[2], proof[1], proof[0]), inputs)
+    with pytest.raises(P.MalformedVerifyingKey):
+        P.prepare_inputs(pvk, inputs + [1])
+
+
+def test_verify_fixture_matches_oracle():
+    """tests/golden/verify.json (written by make_verify_golden.py) still equals what the oracle computes."""
+    with open(os.path.join(GOLDEN, "verify.json")) as f:
+        fx = json.load(f)
+    assert fx["pairing_generators"] == [hex(v) for v in P.to_tower(P.pairing(o.G1_GEN, o.G2_GEN))]
+    for name in GOLDEN_NAMES:
+        vk, proof, inputs = load_vk_and_proof(name)
+        pvk = P.prepare_verifying_key(vk)
+        assert fx[name]["alpha_g1_beta_g2"] == [hex(v) for v in P.to_tower(pvk.alpha_g1_beta_g2)]
+        pi = o.G1.to_affine(P.prepare_inputs(pvk, inputs))
+        assert fx[name]["prepared_inputs"] == o.ser_g1(pi, False).hex()
+
+
+# ---- the device code on the host -------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def hp():
+    out = os.path.join(ROOT, "tests", "_host_pairing.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "host_pairing_shim.cpp")])
+    return ctypes.CDLL(out)
+
+
+def _buf(b):
+    return ctypes.create_string_buffer(b, len(b))
+
+
+def f12_call(hp, op, a, b=None):
+    out = ctypes.create_string_buffer(384)
+    hp.host_f12_op(op, _buf(enc_f12(a)), _buf(enc_f12(b if b is not None else a)), out)
+    return dec_f12(out.raw)
+
+
+def test_generated_constants_are_current():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_pairing_consts", os.path.join(ROOT, "tools", "gen_pairing_consts.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    cs = g.constants()
+    # against the oracle's own derivation
+    want = []
+    for n in (1, 2, 3):
+        for k in range(1, 6):
+            want += list(P._FROB[n][k])
+    want += list(P.TWIST_MUL_BY_Q_X) + list(P.TWIST_MUL_BY_Q_Y) + list(o.G2_B) + [P.TWO_INV]
+    assert cs == want
+    text = open(os.path.join(ROOT, "crescent_credentials_b200", "csrc", "pairing_consts.inc")).read()
+    for v in cs:
+        assert ", ".join("0x%08xu" % l for l in g.limbs(v)) in text
+    pos = sum(1 << i for i in range(64) if P.ATE_LOOP_COUNT[i] == 1)
+    neg = sum(1 << i for i in range(64) if P.ATE_LOOP_COUNT[i] == -1)
+    assert "0x%016xull" % pos in text and "0x%016xull" % neg in text and "0x%016xull" % P.BN_X in text
+
+
+def test_device_fq12_code_on_host_matches_oracle(hp):
+    rng = random.Random(1234)
+    for _ in range(6):
+        a, b = rand_f12(rng), rand_f12(rng)
+        assert f12_call(hp, 0, a, b) == P.f12_mul(a, b)
+        assert f12_call(hp, 1, a) == P.f12_sqr(a)
+        assert f12_call(hp, 2, a) == P.f12_inv(a)
+        assert f12_call(hp, 3, a) == P.f12_conj(a)
+        for n in (1, 2, 3):
+            assert f12_call(hp, 4 + n, a) == P.f12_frobenius(a, n)
+    # sparse operands and the units
+    one = list(P.F12_ONE)
+    assert f12_call(hp, 0, one, one) == one
+    assert f12_call(hp, 2, one) == one
+
+
+def test_device_cyclotomic_code_on_host_matches_oracle(hp):
+    rng = random.Random(77)
+    for _ in range(3):
+        x = rand_f12(rng)
+        c = P.f12_mul(P.f12_conj(x), P.f12_inv(x))           # x^(q^6 - 1)
+        c = P.f12_mul(P.f12_frobenius(c, 2), c)              # ... (q^2 + 1): now in the cyclotomic subgroup
+        assert f12_call(hp, 4, c) == P.f12_sqr(c)
+        assert f12_call(hp, 8, c) == P.f12_pow(c, P.BN_X)
+
+
+def test_device_line_coefficients_on_host_match_oracle(hp):
+    assert hp.host_ell_coeffs() == len(P.g2_prepare(o.G2_GEN)) == 91
+    for k in (1, o.stream_fr(0xE11, 1), o.stream_fr(0xE11, 2)):
+        q = o.G2.mul(o.G2_GEN, k)
+        out = ctypes.create_string_buffer(91 * 192)
+        hp.host_g2_prepare(_buf(enc_g2(q)), out)
+        assert out.raw == enc_coeffs(P.g2_prepare(q))
+
+
+def _miller3(hp, ps, qs):
+    """three pairs through the kernel's loop: pair 0 on the fly, pairs 1 and 2 from tables prepared by the device code"""
+    act = (ctypes.c_int * 3)(*[int(p is not None and q is not None) for p, q in zip(ps, qs)])
+    tabs = []
+    for q in qs[1:]:
+        t = ctypes.create_string_buffer(91 * 192)
+        if q is not None:
+            hp.host_g2_prepare(_buf(enc_g2(q)), t)
+        tabs.append(t)
+    out = ctypes.create_string_buffer(384)
+    hp.host_miller3(_buf(b"".join(enc_g1(p) for p in ps)), act, _buf(enc_g2(qs[0])), tabs[0], tabs[1], out)
+    return out
+
+
+def test_device_miller_loop_and_final_exponentiation_on_host_match_oracle(hp):
+    k = [o.stream_fr(0xF00, i) for i in range(1, 7)]
+    ps = [o.G1.mul(o.G1_GEN, k[0]), o.G1.mul(o.G1_GEN, k[1]), o.G1.mul(o.G1_GEN, k[2])]
+    qs = [o.G2.mul(o.G2_GEN, k[3]), o.G2.mul(o.G2_GEN, k[4]), o.G2.mul(o.G2_GEN, k[5])]
+    cases = [(ps, qs), ([ps[0], None, None], [qs[0], None, None]), ([None, ps[1], ps[2]], [qs[0], qs[1], qs[2]]),
+             ([ps[0], ps[1], None], [None, qs[1], qs[2]])]
+    for p3, q3 in cases:
+        f = _miller3(hp, p3, q3)
+        want = P.multi_miller_loop(p3, q3)
+        assert dec_f12(f.raw) == want
+        out = ctypes.create_string_buffer(384)
+        assert hp.host_final_exp(f, out) == 1
+        assert dec_f12(out.raw) == P.final_exponentiation(want)
+    zero = ctypes.create_string_buffer(384)
+    out = ctypes.create_string_buffer(384)
+    assert hp.host_final_exp(zero, out) == 0  # f = 0: the reference's UnexpectedIdentity branch
+
+
+@pytest.mark.parametrize("name", ["silly", "rand100", "dummy924_nozk"])
+def test_device_verifier_on_host_matches_oracle(hp, name):
+    vk, proof, inputs = load_vk_and_proof(name)
+    pvk = P.prepare_verifying_key(vk)
+    # window tables + prepare_inputs
+    tbl = ctypes.create_string_buffer(len(inputs) * 32 * 255 * 64)
+    for i, b in enumerate(vk.gamma_abc_g1[1:]):
+        t = ctypes.create_string_buffer(32 * 255 * 64)
+        hp.host_abc_table(_buf(enc_g1(b)), t)
+        ctypes.memmove(ctypes.addressof(tbl) + i * 32 * 255 * 64, t, 32 * 255 * 64)
+    x = _buf(b"".join(o.mont_le_bytes(v, o.R_MOD) for v in inputs))
+    pi = ctypes.create_string_buffer(64)
+    hp.host_prepare_inputs(_buf(enc_g1(vk.gamma_abc_g1[0])), tbl, x, ctypes.c_size_t(len(inputs)), pi)
+    want_pi = o.G1.to_affine(P.prepare_inputs(pvk, inputs))
+    assert pi.raw == enc_g1(want_pi)
+    ng = ctypes.create_string_buffer(91 * 192)
+    nd = ctypes.create_string_buffer(91 * 192)
+    hp.host_g2_prepare(_buf(enc_g2(pvk.gamma_g2_neg)), ng)
+    hp.host_g2_prepare(_buf(enc_g2(pvk.delta_g2_neg)), nd)
+    ab = _buf(enc_f12(pvk.alpha_g1_beta_g2))
+    A, B, C = proof
+    assert hp.host_verify_one(_buf(enc_g1(A)), _buf(enc_g2(B)), _buf(enc_g1(C)), pi, ng, nd, ab) == 1
+    assert hp.host_verify_one(_buf(enc_g1(C)), _buf(enc_g2(B)), _buf(enc_g1(A)), pi, ng, nd, ab) == 0
+    bad = o.G1.add(want_pi, o.G1_GEN)
+    assert hp.host_verify_one(_buf(enc_g1(A)), _buf(enc_g2(B)), _buf(enc_g1(C)), _buf(enc_g1(bad)), ng, nd, ab) == 0
