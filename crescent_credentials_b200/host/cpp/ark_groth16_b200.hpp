@@ -41,7 +41,7 @@ namespace ark_groth16_b200 {
 // R1CSResult<T> = Result<T, SynthesisError>: the one SynthesisError raised on the path is thrown as SynthesisError; every
 // other failure (bad sizes, CUDA, out of memory) is a Panic, matching the `.unwrap()`s at creds/src/lib.rs:283.
 struct SynthesisError : std::runtime_error {
-    enum Kind { PolynomialDegreeTooLarge, AssignmentMissing } kind;
+    enum Kind { PolynomialDegreeTooLarge, AssignmentMissing, MalformedVerifyingKey, UnexpectedIdentity } kind;
     SynthesisError(Kind k, const std::string& m) : std::runtime_error(m), kind(k) {}
 };
 struct Panic : std::runtime_error {
@@ -261,6 +261,33 @@ struct Proof {
     std::vector<uint8_t> serialize_compressed() const { return serialize(Compress::Yes); }
     std::vector<uint8_t> serialize_uncompressed() const { return serialize(Compress::No); }
     bool operator==(const Proof& o) const { return a == o.a && b == o.b && c == o.c; }
+    // CanonicalDeserialize::deserialize_uncompressed_unchecked of the 256 bytes Crescent persists (creds/src/utils.rs:140-152):
+    // canonical little-endian coordinates, flags in the top bits of each point's last byte; converted to Montgomery on the host
+    static Proof deserialize_uncompressed_unchecked(const uint8_t* buf, size_t len) {
+        if (len != 256) throw SerializationError("Proof: expected 256 bytes");
+        auto fq = [&](size_t off, bool last) {
+            Limbs v = detail::get_le(buf + off);
+            if (last) v[3] &= (~0ull) >> 2;
+            auto f = Fq::from_bigint(v);
+            if (!f) throw SerializationError("Proof: coordinate not below the modulus");
+            return *f;
+        };
+        auto inf = [&](size_t last_byte) { return (buf[last_byte] & detail::kFlagInfinity) != 0; };
+        Proof r;
+        if (!inf(63)) r.a = G1Affine{fq(0, false), fq(32, true), false};
+        if (!inf(191)) r.b = G2Affine{Fq2{fq(64, false), fq(96, false)}, Fq2{fq(128, false), fq(160, true)}, false};
+        if (!inf(255)) r.c = G1Affine{fq(192, false), fq(224, true), false};
+        return r;
+    }
+    g16_proof to_abi() const {
+        g16_proof p{};
+        auto put = [](uint64_t* w, const Fq& f) { std::memcpy(w, f.v.data(), 32); };
+        if (!a.infinity) put(p.a, a.x), put(p.a + 4, a.y);
+        if (!b.infinity) put(p.b, b.x.c0), put(p.b + 4, b.x.c1), put(p.b + 8, b.y.c0), put(p.b + 12, b.y.c1);
+        if (!c.infinity) put(p.c, c.x), put(p.c + 4, c.y);
+        p.a_inf = a.infinity, p.b_inf = b.infinity, p.c_inf = c.infinity;
+        return p;
+    }
     static Proof from_abi(const g16_proof& p) {
         auto fq = [](const uint64_t* w) { return Fq{Limbs{w[0], w[1], w[2], w[3]}}; };
         Proof r;
@@ -781,6 +808,135 @@ class Groth16 {
     const ConstraintMatrices* loaded_matrices_ = nullptr;
     std::shared_ptr<const R1CS> cached_r1cs_;
     std::unique_ptr<ConstraintMatrices> cached_matrices_;
+};
+
+// ---- the verifier (forks/groth16/src/verifier.rs; scope row f-4) ------------------------------------------------------------------------
+// PreparedVerifyingKey (data_structures.rs:62-72): gamma_g2_neg_pc and delta_g2_neg_pc are line-coefficient tables that live
+// on the device; the host keeps alpha_g1_beta_g2 (an Fq12 as 12 Montgomery Fq in ark-serialize order) and the key it came from.
+struct PreparedVerifyingKey {
+    VerifyingKey vk;
+    int encoding = G16_ENC_MONTGOMERY;
+    std::array<Fq, 12> alpha_g1_beta_g2{};
+    size_t num_public_inputs() const { return vk.gamma_abc_g1.size() - 1; }
+    std::vector<uint8_t> alpha_g1_beta_g2_bytes() const {  // CanonicalSerialize of the Fq12: 12 x 32 canonical LE bytes
+        std::vector<uint8_t> out;
+        for (const Fq& f : alpha_g1_beta_g2) detail::put_le(out, f.into_bigint());
+        return out;
+    }
+};
+
+// Verification bound to one GPU.  One call of verify_proofs checks n (proof, public inputs) pairs, one device thread per
+// proof; every verdict is what the reference's verify_proof returns for that pair.
+class Groth16Verifier {
+  public:
+    explicit Groth16Verifier(int device = 0, void* stream = nullptr) : ctx_(device, stream) {}
+
+    // verifier.rs:13-20.  `encoding` describes vk's words (G16_ENC_CANONICAL for a key read from arkworks bytes).
+    PreparedVerifyingKey prepare_verifying_key(const VerifyingKey& vk, int encoding) {
+        std::lock_guard<std::mutex> g(mu_);
+        PreparedVerifyingKey pvk;
+        pvk.vk = vk;
+        pvk.encoding = encoding;
+        load(pvk);
+        uint64_t gt[48];
+        ctx_.check(g16_vk_alpha_beta(ctx_.get(), gt), "g16_vk_alpha_beta");
+        for (int i = 0; i < 12; i++) pvk.alpha_g1_beta_g2[i] = Fq{Limbs{gt[4 * i], gt[4 * i + 1], gt[4 * i + 2], gt[4 * i + 3]}};
+        return pvk;
+    }
+    PreparedVerifyingKey prepare_verifying_key(const ProvingKey& pk) { return prepare_verifying_key(pk.vk, pk.encoding); }
+
+    // verifier.rs:25-39
+    G1Affine prepare_inputs(const PreparedVerifyingKey& pvk, const std::vector<Fr>& public_inputs) {
+        if (public_inputs.size() + 1 != pvk.vk.gamma_abc_g1.size())
+            throw SynthesisError(SynthesisError::MalformedVerifyingKey, "public input count != gamma_abc_g1.len() - 1");
+        std::lock_guard<std::mutex> g(mu_);
+        ensure(pvk);
+        uint64_t out[8];
+        ctx_.check(g16_prepare_inputs(ctx_.get(), reinterpret_cast<const uint64_t*>(public_inputs.data()), 1, out), "g16_prepare_inputs");
+        bool inf = true;
+        for (uint64_t w : out) inf = inf && w == 0;
+        if (inf) return G1Affine::identity();
+        return G1Affine{Fq{Limbs{out[0], out[1], out[2], out[3]}}, Fq{Limbs{out[4], out[5], out[6], out[7]}}, false};
+    }
+
+    // verifier.rs:44-65
+    bool verify_proof_with_prepared_inputs(const PreparedVerifyingKey& pvk, const Proof& proof, const G1Affine& prepared_inputs) {
+        std::lock_guard<std::mutex> g(mu_);
+        ensure(pvk);
+        g16_proof p = proof.to_abi();
+        uint64_t pi[8] = {};
+        if (!prepared_inputs.infinity) {
+            std::memcpy(pi, prepared_inputs.x.v.data(), 32);
+            std::memcpy(pi + 4, prepared_inputs.y.v.data(), 32);
+        }
+        uint8_t verdict = 0;
+        ctx_.check(g16_verify_batch_prepared(ctx_.get(), &p, pi, 1, &verdict), "g16_verify_batch_prepared");
+        return decide(verdict);
+    }
+
+    // verifier.rs:69-76
+    bool verify_proof(const PreparedVerifyingKey& pvk, const Proof& proof, const std::vector<Fr>& public_inputs) {
+        return verify_proofs(pvk, {proof}, {public_inputs})[0];
+    }
+
+    // n independent verify_proof calls in one launch
+    std::vector<bool> verify_proofs(const PreparedVerifyingKey& pvk, const std::vector<Proof>& proofs,
+                                    const std::vector<std::vector<Fr>>& public_inputs) {
+        if (proofs.size() != public_inputs.size()) throw Panic(G16_ERR_BAD_ARG, "one public-input vector per proof");
+        const size_t k = pvk.num_public_inputs();
+        std::vector<g16_proof> ps;
+        std::vector<uint64_t> xs;
+        ps.reserve(proofs.size());
+        xs.reserve(proofs.size() * k * 4);
+        for (size_t i = 0; i < proofs.size(); i++) {
+            if (public_inputs[i].size() != k)
+                throw SynthesisError(SynthesisError::MalformedVerifyingKey, "public input count != gamma_abc_g1.len() - 1");
+            ps.push_back(proofs[i].to_abi());
+            for (const Fr& x : public_inputs[i]) xs.insert(xs.end(), x.v.begin(), x.v.end());
+        }
+        std::vector<bool> out(proofs.size());
+        if (proofs.empty()) return out;
+        std::vector<uint8_t> verdict(proofs.size());
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            ensure(pvk);
+            ctx_.check(g16_verify_batch(ctx_.get(), ps.data(), k ? xs.data() : nullptr, ps.size(), verdict.data()), "g16_verify_batch");
+        }
+        for (size_t i = 0; i < verdict.size(); i++) out[i] = decide(verdict[i]);
+        return out;
+    }
+    uint64_t launch_count() const { return g16_launch_count(ctx_.get()); }
+    Context& context() { return ctx_; }
+
+  private:
+    static bool decide(uint8_t verdict) {
+        if (verdict == G16_VERDICT_UNEXPECTED_IDENTITY) throw SynthesisError(SynthesisError::UnexpectedIdentity, "final exponentiation of zero");
+        return verdict == G16_VERDICT_ACCEPT;
+    }
+    static std::vector<uint64_t> key_words(const PreparedVerifyingKey& pvk) {
+        std::vector<uint64_t> k{(uint64_t)pvk.encoding};
+        for (const PointVec* p : {&pvk.vk.alpha_g1, &pvk.vk.beta_g2, &pvk.vk.gamma_g2, &pvk.vk.delta_g2, &pvk.vk.gamma_abc_g1})
+            k.insert(k.end(), p->w.begin(), p->w.end());
+        return k;
+    }
+    void load(const PreparedVerifyingKey& pvk) {
+        if (pvk.vk.alpha_g1.size() != 1 || pvk.vk.beta_g2.size() != 1 || pvk.vk.gamma_g2.size() != 1 || pvk.vk.delta_g2.size() != 1 ||
+            pvk.vk.gamma_abc_g1.size() == 0)
+            throw SynthesisError(SynthesisError::MalformedVerifyingKey, "verifying key is missing a point");
+        g16_vk_view v{};
+        v.alpha_g1 = pvk.vk.alpha_g1.data(), v.beta_g2 = pvk.vk.beta_g2.data(), v.gamma_g2 = pvk.vk.gamma_g2.data();
+        v.delta_g2 = pvk.vk.delta_g2.data(), v.gamma_abc_g1 = pvk.vk.gamma_abc_g1.data(), v.gamma_abc_len = pvk.vk.gamma_abc_g1.size();
+        v.encoding = pvk.encoding;
+        ctx_.check(g16_ctx_load_vk(ctx_.get(), &v), "g16_ctx_load_vk");
+        loaded_ = key_words(pvk);
+    }
+    // the device holds one prepared key: a pvk other than the one loaded last is prepared again on first use
+    void ensure(const PreparedVerifyingKey& pvk) {
+        if (loaded_.empty() || loaded_ != key_words(pvk)) load(pvk);
+    }
+    Context ctx_;
+    std::mutex mu_;
+    std::vector<uint64_t> loaded_;
 };
 
 // ---- MSM-sharded proving inside one process: one context (and one host thread per call) per shard ------------------------------------------

@@ -132,6 +132,55 @@ static int run_prove(const Args& a) {
     return 0;
 }
 
+// verify: arkworks pk bytes (the vk is its prefix), 256-byte uncompressed proofs, public inputs as hex -> one verdict per proof.
+//   g16_cli verify --pk key.bin --proof p1.bin[,p2.bin...] --inputs hex,hex,...[;hex,hex,...]  [--gt-out file]
+// Prints "1"/"0" per proof on stdout (verify_proof, verifier.rs:69-76) and the hex of alpha_g1_beta_g2 on stderr.
+static std::vector<std::string> split(const std::string& s, char sep) {
+    std::vector<std::string> out;
+    std::string cur;
+    for (char c : s) {
+        if (c == sep) {
+            out.push_back(cur);
+            cur.clear();
+        } else
+            cur.push_back(c);
+    }
+    out.push_back(cur);
+    return out;
+}
+static int run_verify(const Args& a) {
+    ProvingKey pk = ProvingKey::deserialize_uncompressed_unchecked(read_file(a.req("pk")));
+    Groth16Verifier ver(std::stoi(a.get("device", "0")));
+    PreparedVerifyingKey pvk = ver.prepare_verifying_key(pk);
+    std::vector<Proof> proofs;
+    for (const std::string& f : split(a.req("proof"), ',')) {
+        std::vector<uint8_t> b = read_file(f);
+        proofs.push_back(Proof::deserialize_uncompressed_unchecked(b.data(), b.size()));
+    }
+    std::vector<std::vector<Fr>> inputs;
+    for (const std::string& row : split(a.get("inputs", ""), ';')) {
+        std::vector<Fr> x;
+        if (!row.empty())
+            for (const std::string& h : split(row, ',')) x.push_back(fr_from_hex(h));
+        inputs.push_back(x);
+    }
+    while (inputs.size() < proofs.size()) inputs.push_back(inputs.back());  // one input row for all proofs
+    if (a.has("gt-out")) write_file(a.req("gt-out"), pvk.alpha_g1_beta_g2_bytes());
+    if (a.has("prepared-out")) {
+        std::vector<uint8_t> out;
+        serialize_g1(ver.prepare_inputs(pvk, inputs[0]), Compress::No, out);
+        write_file(a.req("prepared-out"), out);
+    }
+    std::vector<bool> ok = ver.verify_proofs(pvk, proofs, inputs);
+    // the single-proof entry points must agree with the batch
+    if (ver.verify_proof(pvk, proofs[0], inputs[0]) != ok[0] ||
+        ver.verify_proof_with_prepared_inputs(pvk, proofs[0], ver.prepare_inputs(pvk, inputs[0])) != ok[0])
+        throw std::runtime_error("verify_proof disagrees with verify_proofs");
+    for (bool v : ok) std::cout << (v ? "1" : "0") << "\n";
+    fprintf(stderr, "g16_cli: %llu kernel launches\n", (unsigned long long)ver.launch_count());
+    return 0;
+}
+
 template <class QAP>
 static int run_witness_map(const Args& a) {
     R1CS r1cs = R1CS::from_file(R1CSFile::read(read_file(a.req("r1cs"))));
@@ -154,13 +203,14 @@ static int run_witness_map(const Args& a) {
 
 int main(int argc, char** argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: g16_cli (prove|witness-map|rng|rand-fr|r1cs|pk-roundtrip|proof-ser|fp) ...  (see g16_cli.cpp)\n");
+        fprintf(stderr, "usage: g16_cli (prove|verify|witness-map|rng|rand-fr|r1cs|pk-roundtrip|proof-ser|fp) ...  (see g16_cli.cpp)\n");
         return 64;
     }
     std::string cmd = argv[1];
     try {
         Args a = parse(argc, argv, 2);
         if (cmd == "prove") return a.get("reduction", "libsnark") == "circom" ? run_prove<CircomReduction>(a) : run_prove<LibsnarkReduction>(a);
+        if (cmd == "verify") return run_verify(a);
         if (cmd == "witness-map")
             return a.get("reduction", "libsnark") == "circom" ? run_witness_map<CircomReduction>(a) : run_witness_map<LibsnarkReduction>(a);
         if (cmd == "rng" || cmd == "rand-fr") {

@@ -237,3 +237,33 @@ def test_cpp_seeded_rng_prove_equals_python_host_with_same_rng(cli, tmp_path):
         prover.close()
     assert out.stdout.strip() == proof.serialize_compressed().hex()
     assert out.stdout.strip() != meta["proof_compressed"]  # different (r, s) than the fixture's
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_cpp_verify_matches_oracle_verdicts(cli, tmp_path, name):
+    """Groth16Verifier (verifier.rs mirror): arkworks pk bytes + uncompressed proof bytes + public inputs in, one verdict per
+    proof out; PreparedVerifyingKey.alpha_g1_beta_g2 and prepare_inputs byte-identical to tests/golden/verify.json."""
+    import json
+    with open(os.path.join(GOLDEN, "verify.json")) as f:
+        fx = json.load(f)[name]
+    meta, _, _ = load_golden(name)
+    ni = int(meta["num_instance"])
+    good = bytes.fromhex(meta["proof_uncompressed"])
+    swapped = good[192:] + good[64:192] + good[:64]  # A and C exchanged (flags travel with the points)
+    (tmp_path / "good.bin").write_bytes(good)
+    (tmp_path / "swapped.bin").write_bytes(swapped)
+    inputs = ",".join(meta["z"][1:ni])
+    wrong = ",".join([hex((int(meta["z"][1], 16) + 1) % o.R_MOD)] + meta["z"][2:ni]) if ni > 1 else ""
+    rows = ";".join([inputs, inputs, wrong]) if ni > 1 else ""
+    proofs = [tmp_path / "good.bin", tmp_path / "swapped.bin"] + ([tmp_path / "good.bin"] if ni > 1 else [])
+    out = cli("verify", "--pk", os.path.join(GOLDEN, name + ".pk.bin"), "--proof", ",".join(map(str, proofs)), "--inputs", rows,
+              "--gt-out", tmp_path / "gt.bin", "--prepared-out", tmp_path / "pi.bin")
+    assert out.stdout.split() == ["1", "0"] + (["0"] if ni > 1 else [])
+    gt = (tmp_path / "gt.bin").read_bytes()
+    assert [hex(int.from_bytes(gt[i:i + 32], "little")) for i in range(0, 384, 32)] == fx["alpha_g1_beta_g2"]
+    assert (tmp_path / "pi.bin").read_bytes().hex() == fx["prepared_inputs"]
+    # a public-input vector of the wrong length is the reference's MalformedVerifyingKey error, not a verdict
+    bad = cli("verify", "--pk", os.path.join(GOLDEN, name + ".pk.bin"), "--proof", tmp_path / "good.bin",
+              "--inputs", (inputs + ",0x1") if inputs else "0x1", check=False)
+    assert bad.returncode != 0 and "gamma_abc_g1" in bad.stderr
