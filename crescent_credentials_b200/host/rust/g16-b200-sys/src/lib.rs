@@ -39,6 +39,15 @@ extern "C" {
     fn g16_ctx_load_pk(ctx: *mut c_void, pk: *const g16_pk_view, rank: c_int, count: c_int, precompute: c_int) -> c_int;
     fn g16_ctx_load_r1cs(ctx: *mut c_void, r1cs: *const g16_r1cs_view) -> c_int;
     fn g16_prove(ctx: *mut c_void, z: *const u64, r: *const u64, s: *const u64, reduction: c_int, out: *mut g16_proof) -> c_int;
+    fn g16_ctx_load_vk(ctx: *mut c_void, vk: *const g16_vk_view) -> c_int;
+    fn g16_vk_alpha_beta(ctx: *mut c_void, out: *mut u64) -> c_int;
+    fn g16_verify_batch(ctx: *mut c_void, proofs: *const g16_proof, public_inputs: *const u64, n: usize, verdict: *mut u8) -> c_int;
+}
+
+#[repr(C)]
+pub struct g16_vk_view {
+    alpha_g1: *const u64, beta_g2: *const u64, gamma_g2: *const u64, delta_g2: *const u64,
+    gamma_abc_g1: *const u64, gamma_abc_len: usize, encoding: c_int,
 }
 
 const G16_ERR_DEGREE_TOO_LARGE: c_int = 1;
@@ -126,3 +135,55 @@ impl B200Prover {
     }
 }
 impl Drop for B200Prover { fn drop(&mut self) { unsafe { g16_ctx_destroy(self.ctx) } } }
+
+/// Persistent GPU verifier for one VerifyingKey (forks/groth16/src/verifier.rs): `verify_proofs` checks n (proof, inputs)
+/// pairs per call, one device thread per proof, and returns the reference's verdict for each.
+pub struct B200Verifier { ctx: *mut c_void, inputs: usize }
+unsafe impl Send for B200Verifier {}
+
+impl B200Verifier {
+    /// prepare_verifying_key (verifier.rs:13-20) on the device.  The key's fields are passed one by one (data_structures.rs:
+    /// 31-44): this crate cannot name the fork's `VerifyingKey` without a dependency cycle (the fork depends on it).
+    pub fn new(device: i32, alpha_g1: &G1Affine, beta_g2: &G2Affine, gamma_g2: &G2Affine, delta_g2: &G2Affine,
+               gamma_abc_g1: &[G1Affine]) -> Self {
+        let mut ctx = std::ptr::null_mut();
+        let rc = unsafe { g16_ctx_create(&mut ctx, device, std::ptr::null_mut()) };
+        if rc != 0 { panic!("g16_ctx_create: {}", B200Prover::err(std::ptr::null())); }
+        let (mut a, mut b, mut g, mut d, mut abc) = (vec![], vec![], vec![], vec![], vec![]);
+        pack_g1(alpha_g1, &mut a); pack_g2(beta_g2, &mut b); pack_g2(gamma_g2, &mut g); pack_g2(delta_g2, &mut d);
+        gamma_abc_g1.iter().for_each(|p| pack_g1(p, &mut abc));
+        let view = g16_vk_view { alpha_g1: a.as_ptr(), beta_g2: b.as_ptr(), gamma_g2: g.as_ptr(), delta_g2: d.as_ptr(),
+            gamma_abc_g1: abc.as_ptr(), gamma_abc_len: gamma_abc_g1.len(), encoding: 0 };
+        if unsafe { g16_ctx_load_vk(ctx, &view) } != 0 { panic!("g16_ctx_load_vk: {}", B200Prover::err(ctx)); }
+        Self { ctx, inputs: gamma_abc_g1.len() - 1 }
+    }
+    /// PreparedVerifyingKey.alpha_g1_beta_g2 as 12 Montgomery Fq (c0.c0.c0 ... c1.c2.c1).
+    pub fn alpha_g1_beta_g2(&self) -> [u64; 48] {
+        let mut out = [0u64; 48];
+        if unsafe { g16_vk_alpha_beta(self.ctx, out.as_mut_ptr()) } != 0 { panic!("g16_vk_alpha_beta: {}", B200Prover::err(self.ctx)); }
+        out
+    }
+    /// Groth16::verify_proof (verifier.rs:69-76) for every pair; a proof is its (a, b, c) (data_structures.rs:7-14).
+    pub fn verify_proofs(&self, proofs: &[(G1Affine, G2Affine, G1Affine)], public_inputs: &[Vec<Fr>]) -> Result<Vec<bool>, SynthesisError> {
+        assert_eq!(proofs.len(), public_inputs.len());
+        let mut ps = Vec::with_capacity(proofs.len());
+        let mut xs = Vec::with_capacity(proofs.len() * self.inputs * 4);
+        for (p, x) in proofs.iter().zip(public_inputs) {
+            if x.len() != self.inputs { return Err(SynthesisError::MalformedVerifyingKey); }          // verifier.rs:29-31
+            let (mut a, mut b, mut c) = (vec![], vec![], vec![]);
+            pack_g1(&p.0, &mut a); pack_g2(&p.1, &mut b); pack_g1(&p.2, &mut c);
+            let mut q = g16_proof::default();
+            q.a.copy_from_slice(&a); q.b.copy_from_slice(&b); q.c.copy_from_slice(&c);
+            q.a_inf = p.0.is_zero() as i32; q.b_inf = p.1.is_zero() as i32; q.c_inf = p.2.is_zero() as i32;
+            ps.push(q);
+            x.iter().for_each(|v| xs.extend_from_slice(&fr_limbs(v)));
+        }
+        let mut verdict = vec![0u8; proofs.len()];
+        if unsafe { g16_verify_batch(self.ctx, ps.as_ptr(), xs.as_ptr(), ps.len(), verdict.as_mut_ptr()) } != 0 {
+            panic!("g16_verify_batch: {}", B200Prover::err(self.ctx));
+        }
+        if verdict.iter().any(|&v| v == 2) { return Err(SynthesisError::UnexpectedIdentity); }       // verifier.rs:62
+        Ok(verdict.iter().map(|&v| v == 1).collect())
+    }
+}
+impl Drop for B200Verifier { fn drop(&mut self) { unsafe { g16_ctx_destroy(self.ctx) } } }
