@@ -196,7 +196,13 @@ def main():
                     help="staggered plan: rank 0's share of the wire MSMs (default: the balance point of sharded.rank0_wire_share)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--what", default="prove", choices=["prove", "verify"],
+                    help="verify: the verification sweep of scope row f-4 (tools/verify_bench.py) with its CPU baseline, one JSON "
+                         "line per batch size; not the headline metric")
+    ap.add_argument("--verify-sizes", type=int, nargs="+", default=[1, 1024, 32768, 131072])
     args = ap.parse_args()
+    if args.what == "verify":
+        return verify_sweep(args)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -473,6 +479,34 @@ def main():
     return 0
 
 
+def verify_sweep(args):
+    """Row f-4: n verify_proof calls per launch (tools/verify_bench.py) beside the CPU restatement of arkworks' verifier
+    (oracle/libg16oracle.so: G2Prepared lines, multi_miller_loop, final exponentiation, one double-and-add mul_bigint per
+    public input) on all host threads over a bounded sample."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("verify_bench", os.path.join(ROOT, "tools", "verify_bench.py"))
+    vb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vb)
+
+    def cpu_baseline(vk_arrays, proofs, x_mont, want):
+        if args.no_cpu_baseline:
+            return None
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import coracle as c  # the checker, timed as the CPU baseline (never on the product path)
+        threads = c.hardware_threads()
+        n = min(proofs.shape[0], 64 * threads)
+        vk = c.vk_struct(*vk_arrays)
+        verdict, secs = c.verify(vk, np.ascontiguousarray(proofs[:n]), np.ascontiguousarray(x_mont[:n]), n, threads)
+        assert (verdict == want[:n]).all(), "CPU verifier disagrees with the constructed verdicts"
+        return {"value": n / secs, "unit": "proofs/s", "cores": threads, "kind": "port",
+                "sample": f"{n} of the same (proof, inputs) pairs, all host threads; CPU restatement of arkworks' verifier, "
+                          "not the arkworks binary", "ms_per_proof_per_core": secs * 1e3 * threads / n}
+
+    vb.run(types.SimpleNamespace(inputs=23, sizes=args.verify_sizes, reps=3, occupancy=[8]), cpu_baseline)
+    return 0
+
+
 def reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference (Rust + un-vendored arkworks
     crates) cannot be compiled in this image, so this times oracle/libg16oracle.so -- the multithreaded C++ restatement
@@ -545,7 +579,7 @@ def reference_arm(args):
               f"N + 2^c additions); CPU restatement of arkworks' algorithm shape (oracle/g16_oracle.cpp), "
               f"not the arkworks binary (no Rust toolchain in this image)")
     out = {"impl": "reference", "metric": METRIC, "value": val_, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "u64x4 (BN254 Fr/Fq Montgomery, exact)", "data": "synthetic",
            "config": {"workload": f"{args.workload} ({args.witness} witness)", "constraints": nc, "wires": m, "domain": n, "nnz": nnz},
            "cpu_baseline": {"value": val_, "unit": UNIT, "cores": th, "kind": "port", "sample": sample},

@@ -171,3 +171,49 @@ def prove(pk, r, z, r_mont, s_mont, reduction=0, want_h=False, threads=0):
         raise RuntimeError(f"oc_prove rc={rc}")
     proof = (np.array(out.a[:], dtype=np.uint64), np.array(out.b[:], dtype=np.uint64), np.array(out.c[:], dtype=np.uint64))
     return proof, h, tm.as_dict()
+
+
+# ---- the verifier (row f-4): pairing / prepare_verifying_key / prepare_inputs / verify_proof -----------------------------------------
+class OcVk(C.Structure):
+    _fields_ = [("alpha_g1", C.c_void_p), ("beta_g2", C.c_void_p), ("gamma_g2", C.c_void_p), ("delta_g2", C.c_void_p),
+                ("gamma_abc_g1", C.c_void_p), ("gamma_abc_len", C.c_size_t)]
+
+
+def vk_struct(alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1):
+    """Montgomery limb arrays (8 / 16 / 16 / 16 words, (len, 8)); the returned struct keeps them alive."""
+    keep = [np.ascontiguousarray(a, dtype=np.uint64) for a in (alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1)]
+    v = OcVk(*[a.ctypes.data for a in keep], keep[4].reshape(-1, 8).shape[0])
+    v._keep = keep
+    return v
+
+
+def pairing(g1_points, g2_points, threads=0):
+    p = np.ascontiguousarray(g1_points, dtype=np.uint64).reshape(-1, 8)
+    q = np.ascontiguousarray(g2_points, dtype=np.uint64).reshape(-1, 16)
+    out = np.zeros((p.shape[0], 48), dtype=np.uint64)
+    lib().oc_pairing(_p(p), _p(q), C.c_size_t(p.shape[0]), _p(out), C.c_int(threads))
+    return out
+
+
+def prepare_vk(vk: OcVk):
+    out = np.zeros(48, dtype=np.uint64)
+    lib().oc_prepare_vk(C.byref(vk), _p(out))
+    return out
+
+
+def prepare_inputs(vk: OcVk, inputs, n, threads=0):
+    x = np.ascontiguousarray(inputs, dtype=np.uint64)
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib().oc_prepare_inputs(C.byref(vk), _p(x) if x.size else None, C.c_size_t(n), _p(out), C.c_int(threads))
+    return out
+
+
+def verify(vk: OcVk, proofs, inputs, n, threads=0):
+    """proofs: (n, 32) uint64 = a | b | c Montgomery affine.  Returns (verdicts uint8[n], seconds of the per-proof part)."""
+    pr = np.ascontiguousarray(proofs, dtype=np.uint64).reshape(n, 32)
+    x = np.ascontiguousarray(inputs, dtype=np.uint64)
+    out = np.zeros(n, dtype=np.uint8)
+    f = lib().oc_verify
+    f.restype = C.c_double
+    secs = f(C.byref(vk), _p(pr), _p(x) if x.size else None, C.c_size_t(n), _p(out), C.c_int(threads))
+    return out, secs

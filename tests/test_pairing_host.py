@@ -261,3 +261,32 @@ def test_device_verifier_on_host_matches_oracle(hp, name):
     assert hp.host_verify_one(_buf(enc_g1(C)), _buf(enc_g2(B)), _buf(enc_g1(A)), pi, ng, nd, ab) == 0
     bad = o.G1.add(want_pi, o.G1_GEN)
     assert hp.host_verify_one(_buf(enc_g1(A)), _buf(enc_g2(B)), _buf(enc_g1(C)), _buf(enc_g1(bad)), ng, nd, ab) == 0
+
+
+# ---- the C++ oracle (64-bit limbs, arkworks' shape; the CPU baseline of tools/verify_bench.py) against the big-integer one ------
+def test_cpp_oracle_pairing_and_verifier_match_python_oracle():
+    import coracle as c
+    from crescent_credentials_b200 import groth16 as g
+    ks = [(1, 1), (o.stream_fr(0x9A1, 1), o.stream_fr(0x9A1, 2)), (o.R_MOD - 1, 2)]
+    ps = [o.G1.mul(o.G1_GEN, a) for a, _ in ks] + [None]
+    qs = [o.G2.mul(o.G2_GEN, b) for _, b in ks] + [o.G2_GEN]
+    got = c.pairing(g.g1_points_to_mont(ps), g.g2_points_to_mont(qs), threads=2)
+    for row, p, q in zip(got, ps, qs):
+        assert g.fq_from_mont(row.reshape(-1, 4)) == P.to_tower(P.pairing(p, q))
+    for name in ["silly", "rand100", "rand300", "dummy924_nozk"]:
+        vk, proof, inputs = load_vk_and_proof(name)
+        pvk = P.prepare_verifying_key(vk)
+        cvk = c.vk_struct(g.g1_points_to_mont([vk.alpha_g1]), g.g2_points_to_mont([vk.beta_g2]), g.g2_points_to_mont([vk.gamma_g2]),
+                          g.g2_points_to_mont([vk.delta_g2]), g.g1_points_to_mont(vk.gamma_abc_g1))
+        assert g.fq_from_mont(c.prepare_vk(cvk).reshape(-1, 4)) == P.to_tower(pvk.alpha_g1_beta_g2)
+        A, B, C_ = proof
+        cases = [((A, B, C_), inputs), ((C_, B, A), inputs), ((None, B, C_), inputs), ((A, B, None), inputs)]
+        if inputs:
+            cases.append(((A, B, C_), [(inputs[0] + 5) % o.R_MOD] + list(inputs[1:])))
+        pr = np.concatenate([np.concatenate([g.g1_points_to_mont([a]).reshape(-1), g.g2_points_to_mont([b]).reshape(-1),
+                                             g.g1_points_to_mont([cc]).reshape(-1)]) for (a, b, cc), _ in cases]).reshape(len(cases), 32)
+        xs = g.fr_to_mont([v for _, x in cases for v in x]) if inputs else np.zeros((0, 4), dtype=np.uint64)
+        verdict, _ = c.verify(cvk, pr, xs, len(cases), threads=2)
+        assert [bool(v == 1) for v in verdict] == [P.verify_proof(pvk, pr_, x) for pr_, x in cases]
+        pi = c.prepare_inputs(cvk, xs[:len(inputs)], 1)
+        assert g.g1_from_mont(pi[0]) == o.G1.to_affine(P.prepare_inputs(pvk, inputs))

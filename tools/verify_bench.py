@@ -46,7 +46,11 @@ def main():
     ap.add_argument("--sizes", type=int, nargs="+", default=[1, 64, 1024, 8192, 32768])
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--occupancy", type=int, nargs="+", default=[8])
-    args = ap.parse_args()
+    run(ap.parse_args())
+
+
+def run(args, cpu_baseline=None):
+    """cpu_baseline (bench.py --what verify only): callable(vk_arrays, proofs (n, 32), inputs (n, k, 4), want) -> dict."""
     torch.cuda.set_device(0)
     stream = torch.cuda.Stream()  # a real (non-null) stream: the library orders its work on it and the events see it
     torch.cuda.set_stream(stream)
@@ -58,7 +62,8 @@ def main():
     g1 = lambda ks: ctx.fixed_base(1, g.fr_to_mont(ks))
     g2 = lambda ks: ctx.fixed_base(2, g.fr_to_mont(ks))
     t0 = time.time()
-    ctx.load_vk(g1([alpha])[0], g2([beta])[0], g2([gamma])[0], g2([delta])[0], g1(abc))
+    vk_arrays = (g1([alpha])[0], g2([beta])[0], g2([gamma])[0], g2([delta])[0], g1(abc))
+    ctx.load_vk(*vk_arrays)
     ctx.sync()
     load_s = time.time() - t0
     nmax = max(args.sizes)
@@ -75,6 +80,7 @@ def main():
     proofs[:, 0:8], proofs[:, 8:24], proofs[:, 24:32] = A, B, Cc
     x_mont = g.fr_to_mont([v for row in xs for v in row]).reshape(nmax, k, 4)
     want = (~bad).astype(np.uint8)
+    cpu = cpu_baseline(vk_arrays, proofs[:, :32], x_mont, want) if cpu_baseline else None
     d_proofs = ctx.dev_alloc(proofs.nbytes)
     d_x = ctx.dev_alloc(max(x_mont.nbytes, 8))
     d_v = ctx.dev_alloc(nmax)
@@ -103,7 +109,7 @@ def main():
         print(json.dumps({"what": "groth16_verify_batch", "proofs": n, "public_inputs": k, "verify_occupancy": occ, "device_ms": round(d, 3),
                           "device_proofs_per_s": round(n / d * 1e3, 1), "e2e_ms": round(e, 3), "e2e_proofs_per_s": round(n / e * 1e3, 1),
                           "h2d_bytes": int(n * (272 + 32 * k)), "d2h_bytes": n, "verdicts_checked": True,
-                          "vk_load_s": round(load_s, 3)}), flush=True)
+                          "vk_load_s": round(load_s, 3), "cpu_baseline": cpu}), flush=True)
     ctx.close()
 
 
