@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--ba-levels", type=int, default=-1, help="batched-affine levels before the XYZZ tail (-1 = library default)")
     ap.add_argument("--share-digits", type=int, default=1)
+    ap.add_argument("--opt", nargs="*", default=[], help="extra library options, key=value (e.g. asm_tables=0)")
     ap.add_argument("--main-priority", type=int, default=0, help="priority of the torch stream the library uses as its main stream")
     ap.add_argument("--inflight", type=int, default=2,
                     help="extra timed region with this many proofs in flight on one GPU (separate contexts, one host thread "
@@ -233,6 +234,9 @@ def main():
     ctx.load_r1cs(inst.nc, inst.ni, inst.m, inst.matrices.row_ptr, inst.matrices.col, inst.matrices.val, inst.matrices.encoding)
     ctx.set_option("ba_levels", args.ba_levels)
     ctx.set_option("share_digits", args.share_digits)
+    for kv in args.opt:
+        k_, v_ = kv.split("=")
+        ctx.set_option(k_, int(v_))
     from crescent_credentials_b200 import sharded
     h_len = int(np.asarray(pk.arrays["h_query"]).reshape(-1, 8).shape[0])
     m1 = int(np.asarray(pk.arrays["a_query"]).reshape(-1, 8).shape[0]) - 1

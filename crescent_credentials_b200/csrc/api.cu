@@ -137,6 +137,7 @@ void g16_ctx_destroy(g16_ctx* ctx) {
     }
     verify_free(ctx);
     dev_free(ctx->d_small);
+    dev_free(ctx->d_asm_tables);
     dev_free(ctx->d_partial);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < kSideStreams; i++) {
@@ -526,6 +527,7 @@ static int load_pk_ranges(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, i
     load_fq(&ctx->a0.x, pk->a_query, 2, enc);          // query[0]: the constant-1 wire (prover.rs:265)
     load_fq(&ctx->b1_0.x, pk->b_g1_query, 2, enc);
     load_fq(&ctx->b2_0.x.c0, pk->b_g2_query, 4, enc);
+    G16_TRY(assemble_build_tables(ctx, ctx->main));
     auto range = [&](size_t total, size_t* lo, size_t* hi) {
         *lo = total * (size_t)shard_rank / (size_t)shard_count;
         *hi = total * (size_t)(shard_rank + 1) / (size_t)shard_count;
@@ -1004,6 +1006,7 @@ int g16_set_option(g16_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "wm_priority")) ctx->opt_wm_priority = value;
     else if (!strcmp(key, "ba_prefetch")) ctx->opt_ba_prefetch = value;
     else if (!strcmp(key, "verify_occupancy")) ctx->opt_verify_occupancy = value;
+    else if (!strcmp(key, "asm_tables")) ctx->opt_asm_tables = value;
     else return set_err(ctx, G16_ERR_BAD_ARG, "unknown option '%s'", key);
     return G16_OK;
 }

@@ -65,6 +65,104 @@ __global__ void k_assemble_pre(AsmConsts k, Scalar256 r, Scalar256 s, Scalar256 
     }
 }
 
+// ---- the same (r, s, pk)-only points from per-key fixed-base tables -------------------------------------------------------
+// Every scalar multiplication of k_assemble_pre has a base that depends on the key alone once the products are expanded:
+//   T_a = r*delta_g1 + U,  s*T_a = (rs)*delta_g1 + s*U,  r*T_b = (rs)*delta_g1 + r*V,  T_b2 = s*delta_g2 + W
+// with U = a_query[0] + alpha_g1, V = b_g1_query[0] + beta_g1, W = b_g2_query[0] + beta_g2.  With 2^(8j) * base, j < 32, stored
+// per key (10 KB), one warp computes a 254-bit multiple with every lane working on one byte of the scalar (8 doublings and at
+// most 8 mixed additions) and a 5-step tree sum: ~250 dependent field products instead of ~4000.  Large circuits never saw
+// this kernel (it hides under the MSMs); for the ~1 k-constraint circuits the reference also proves (creds/src/rangeproof.rs:
+// 490-511, creds/benches/proof_benchmark.rs:85-96) it was the floor of the proof latency: 4.4 ms.
+struct AsmTables {
+    G1Affine d1[32], u[32], v[32];  // 2^(8j) * {delta_g1, U, V}
+    G2Affine d2[32];                // 2^(8j) * delta_g2
+    G2Affine w;                     // W
+};
+
+__global__ void k_asm_tables(AsmConsts k, AsmTables* out) {
+    const unsigned t = threadIdx.x, j = t & 31, which = t >> 5;
+    uint32_t e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    e[j >> 2] = 1u << (8 * (j & 3));
+    if (which < 3) {
+        G1XYZZ b = G1XYZZ::from_affine(which == 0 ? k.delta_g1 : which == 1 ? k.a0 : k.b1_0);
+        if (which == 1) b.madd(k.alpha_g1);
+        if (which == 2) b.madd(k.beta_g1);
+        G1Affine p = scalar_mul(b, e).to_affine();
+        (which == 0 ? out->d1 : which == 1 ? out->u : out->v)[j] = p;
+    } else {
+        out->d2[j] = scalar_mul(G2XYZZ::from_affine(k.delta_g2), e).to_affine();
+        if (j == 0) {
+            G2XYZZ w = G2XYZZ::from_affine(k.b2_0);
+            w.madd(k.beta_g2);
+            out->w = w.to_affine();
+        }
+    }
+}
+
+// byte j of the scalar times tbl[j] (= 2^(8j) * base)
+template <class F>
+__device__ __forceinline__ XYZZ<F> byte_mul(const Affine<F>& p, uint32_t byte) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+#pragma unroll 1
+    for (int bit = 7; bit >= 0; bit--) {
+        acc = acc.dbl();
+        if ((byte >> bit) & 1u) acc.madd(p);
+    }
+    return acc;
+}
+template <class F>
+__device__ __forceinline__ void warp_tree_sum(XYZZ<F>* sh, unsigned lane) {  // sh[0] = sum of the 32 entries
+#pragma unroll 1
+    for (unsigned off = 16; off >= 1; off >>= 1) {
+        __syncwarp();
+        if (lane < off) {
+            XYZZ<F> a = sh[lane];
+            a.add(sh[lane + off]);
+            sh[lane] = a;
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(160) k_assemble_pre_tables(const AsmTables* __restrict__ T, Scalar256 r, Scalar256 s, Scalar256 rs,
+                                                             int r_is_zero, AsmPre* out) {
+    __shared__ G1XYZZ sh1[4][32];  // r*delta_g1, rs*delta_g1, s*U, r*V
+    __shared__ G2XYZZ sh2[32];     // s*delta_g2
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    auto byte_of = [&](const Scalar256& k) { return (k.w[lane >> 2] >> (8 * (lane & 3))) & 0xffu; };
+    if (wid < 4) {
+        const Scalar256& k = wid == 0 ? r : wid == 1 ? rs : wid == 2 ? s : r;
+        const G1Affine* tbl = wid <= 1 ? T->d1 : wid == 2 ? T->u : T->v;
+        sh1[wid][lane] = byte_mul(tbl[lane], byte_of(k));
+        warp_tree_sum(sh1[wid], lane);
+    } else {
+        sh2[lane] = byte_mul(T->d2[lane], byte_of(s));
+        warp_tree_sum(sh2, lane);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        G1XYZZ t = sh1[0][0];
+        t.madd(T->u[0]);  // U
+        out->t_a = t;
+    } else if (threadIdx.x == 32) {
+        G1XYZZ t = sh1[1][0];
+        out->rs_d1 = t;
+        t.add(sh1[2][0]);
+        out->s_ta = t;
+    } else if (threadIdx.x == 64) {
+        G1XYZZ t = G1XYZZ::inf();
+        if (!r_is_zero) {  // prover.rs:102
+            t = sh1[1][0];
+            t.add(sh1[3][0]);
+        }
+        out->r_tb = t;
+    } else if (threadIdx.x == 128) {
+        G2XYZZ t = sh2[0];
+        t.madd(T->w);
+        out->t_b2 = t;
+    }
+}
+
 // out = k * in for one G1 point (one lane; latency-bound, runs beside the remaining MSMs)
 __global__ void k_scale_point(const G1XYZZ* __restrict__ in, Scalar256 k, G1XYZZ* __restrict__ out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *out = scalar_mul(*in, k.w);
@@ -138,9 +236,21 @@ static AsmPre* pre_ptr(g16_ctx* ctx) { return (AsmPre*)ctx->d_small; }
 static ProofDev* proof_ptr(g16_ctx* ctx) { return (ProofDev*)((char*)ctx->d_small + 1024); }
 static void* affine_ptr(g16_ctx* ctx) { return (char*)ctx->d_small + 2048; }
 
+// per-key tables for k_assemble_pre_tables; called by g16_ctx_load_pk once the single points are in the context
+int assemble_build_tables(g16_ctx* ctx, cudaStream_t st) {
+    if (!ctx->d_asm_tables) G16_CUDA(ctx, cudaMalloc(&ctx->d_asm_tables, sizeof(AsmTables)));
+    G16_LAUNCH(ctx, k_asm_tables, 1, 128, 0, st, consts_of(ctx), (AsmTables*)ctx->d_asm_tables);
+    return G16_OK;
+}
+
 int assemble_pre(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, cudaStream_t st) {
     Fr rm = fr_load(r), sm = fr_load(s);
     Fr rs = rm * sm;
+    if (ctx->opt_asm_tables && ctx->d_asm_tables) {
+        G16_LAUNCH(ctx, k_assemble_pre_tables, 1, 160, 0, st, (const AsmTables*)ctx->d_asm_tables, canon(rm), canon(sm), canon(rs),
+                   (int)rm.is_zero(), pre_ptr(ctx));
+        return G16_OK;
+    }
     G16_LAUNCH(ctx, k_assemble_pre, 1, 128, 0, st, consts_of(ctx), canon(rm), canon(sm), canon(rs), (int)rm.is_zero(), pre_ptr(ctx));
     return G16_OK;
 }

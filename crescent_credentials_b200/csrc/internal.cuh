@@ -151,6 +151,8 @@ struct g16_ctx {
     g16::G2Affine beta_g2, delta_g2, b2_0;
     void* d_partial = nullptr;  // g16_partial on the device
     void* d_small = nullptr;    // small device scratch for assembly
+    void* d_asm_tables = nullptr;  // assemble.cu: per-key fixed-base tables of the (r, s)-only scalar multiplications
+    int opt_asm_tables = 1;        // 0: the single-lane double-and-add k_assemble_pre
     g16_timings tm = {};
     int opt_serialize = 0, opt_kernel_events = 0, opt_window_bits = 0, opt_acc_variant = 0;
     int opt_ba_levels = -1;  // batched-affine levels (-1 = default)
@@ -265,6 +267,7 @@ int fixed_base_dev(g16_ctx* ctx, int group, const Fr* scalars_dev, size_t n, voi
 
 // assemble.cu -----------------------------------------------------------------------------------------------------------
 int assemble_pre(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, cudaStream_t st);
+int assemble_build_tables(g16_ctx* ctx, cudaStream_t st);
 G1Affine g1_generator();
 G2Affine g2_generator();
 // out = k * in for one G1 XYZZ point on the device (k: Montgomery Fr on the host)

@@ -196,6 +196,8 @@ int g16_get_timings(g16_ctx* ctx, g16_timings* out);
  * "ntt_radix4" = 0 / 1 forces the radix-2 / radix-4 transform passes (default -1: radix-4 only when no MSM runs beside),
  * "spmv_sell" = 0 selects the row-per-thread CSR kernel instead of the sliced-ELL one (default 1),
  * "ba_prefetch" = 1 / 2 selects the cp.async / L2-prefetch variants of k_ba_add (default 0; both measured slower),
+ * "asm_tables" = 0 computes the (r, s)-only points of the assembly with one lane per scalar multiplication instead of the
+ *   per-key fixed-base tables (default 1; matters for small circuits only: 4.4 ms -> 0.3 ms of latency),
  * "verify_occupancy" = 8 / 12 / 16 selects the k_verify build for that many resident warps per SM (255 / 168 / 128 registers).
  * No option changes a result bit.  Unknown keys return G16_ERR_BAD_ARG. */
 int g16_set_option(g16_ctx* ctx, const char* key, int value);

@@ -338,6 +338,42 @@ def test_golden_prove_stream_plans(split, prio):
             prover.close()
 
 
+@pytest.mark.parametrize("tables", [0, 1])
+def test_golden_prove_assembly_fixed_base_tables(tables):
+    """The (r, s)-only points of the assembly from the per-key fixed-base tables (one scalar byte per lane + tree sum) or
+    from single-lane double-and-add: same proof bytes for every fixture, including r = s = 0 (B-in-G1 skipped, prover.rs:102),
+    and for (r, s) with zero and all-ones bytes."""
+    for name in GOLDEN_NAMES:
+        meta, r1cs_bytes, pk_bytes = load_golden(name)
+        mats = load_matrices(r1cs_bytes)
+        pk = g.ProvingKey.deserialize_uncompressed_unchecked(pk_bytes)
+        prover = g.Groth16(0, qap=g.CircomReduction if meta["reduction"] == "circom" else g.LibsnarkReduction)
+        prover.ctx.set_option("asm_tables", tables)
+        try:
+            z = [int(v, 16) for v in meta["z"]]
+            proof = prover.create_proof_with_reduction_and_matrices(pk, int(meta["r"], 16), int(meta["s"], 16), mats,
+                                                                    mats.num_instance_variables, mats.num_constraints, z)
+            assert proof.serialize_uncompressed().hex() == meta["proof_uncompressed"], name
+            if name == "rand100":  # scalars with empty / full bytes, r = 0 with s != 0 and the reverse: against the other variant
+                from crescent_credentials_b200 import verifier as v
+                other = g.Groth16(0)
+                other.ctx.set_option("asm_tables", 1 - tables)
+                ver = v.Verifier(0)
+                try:
+                    pvk = ver.prepare_verifying_key(pk)
+                    public = z[1:mats.num_instance_variables]
+                    for r, s in [(0, 5), (7, 0), (1 << 248, (1 << 253) + 255), (o.R_MOD - 1, 0xFF00FF00FF << 100), (0xFF, 1 << 8)]:
+                        args = (pk, r, s, mats, mats.num_instance_variables, mats.num_constraints, z)
+                        p1 = prover.create_proof_with_reduction_and_matrices(*args)
+                        assert p1.serialize_uncompressed() == other.create_proof_with_reduction_and_matrices(*args).serialize_uncompressed()
+                        assert ver.verify_proof(pvk, p1, public) is True  # any (r, s) gives a valid proof of the same statement
+                finally:
+                    other.close()
+                    ver.close()
+        finally:
+            prover.close()
+
+
 def test_spmv_sliced_ell_ragged_rows(gpu_ctx):
     """Sliced-ELL SpMV (rows sorted by length, 32 per slice, +1 / -1 classes in the column word) against the oracle's
     evaluate_constraint and against the row-per-thread CSR kernel: empty rows, rows longer than a slice, repeated wires in
