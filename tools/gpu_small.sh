@@ -16,8 +16,8 @@ run S-2^12 t1_ba0 --opt asm_tables=1 --ba-levels 0
 run S-2^12 t1_nopre --opt asm_tables=1 --precompute 0
 run S-2^12 t1_ba0_nopre --opt asm_tables=1 --ba-levels 0 --precompute 0
 run S-2^12 t1_noshare --opt asm_tables=1 --share-digits 0
-run S-2^16 t1 --opt asm_tables=1
-run S-2^16 t1_ba0 --opt asm_tables=1 --ba-levels 0
+run S-2^16 t1_2^16 --opt asm_tables=1
+run S-2^16 t1_ba0_2^16 --opt asm_tables=1 --ba-levels 0
 timeout 200 python bench.py --no-cpu-baseline --inflight 0 > gpurun_out/small_rs256.json 2>/dev/null; python -c "
 import json
 d=json.loads(open('gpurun_out/small_rs256.json').read().strip().splitlines()[-1]); print('S-rs256', d['ms_per_step'], d['e2e']['ms_per_step'])"
