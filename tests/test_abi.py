@@ -48,7 +48,7 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 src = open(os.path.join(dirpath, fn)).read()
                 # comments may cite the oracle; code may not import, include, link or dlopen it
-                assert not re.search(r"^\s*(import|from)\s+(pyref|coracle|oracle)\b", src, re.M), fn
+                assert not re.search(r"^\s*(import|from)\s+(pyref|coracle|oracle|pairing)\b", src, re.M), fn
                 assert not re.search(r"#include\s*[<\"][^>\"]*oracle", src), fn
                 assert "libg16oracle" not in src and "CDLL(" not in src.replace("C.CDLL(LIB_PATH)", ""), fn
 
