@@ -12,6 +12,11 @@
 //   g16_cli pk-roundtrip IN OUT                 deserialize_uncompressed_unchecked -> serialize_uncompressed
 //   g16_cli proof-ser AX AY BX0 BX1 BY0 BY1 CX CY    canonical coordinates ("inf" for a point: AX=inf AY=-)
 //   g16_cli fp (fr|fq) (from|into) HEX          host Montgomery marshalling check
+//   g16_cli r1cs-write --prefix P --nc N --nwires M --ninputs L --out F    CSR dumps (P.{0,1,2}.{ptr,col,val}) -> iden3 .r1cs
+//   g16_cli pk-write --prefix P --out F          canonical point dumps (P.<field>.bin) -> arkworks uncompressed ProvingKey bytes
+//   g16_cli r1cs-bench F                         R1CSFile::read + R1CS::to_matrices timings (scope row f-1)
+// r1cs-write / pk-write exist so that full-size fixtures in the reference's FILE formats can be produced from the synthetic
+// instance of bench.py (tools/next_rows_bench.py): the prove command then runs the drop-in flow end to end on them.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -79,10 +84,120 @@ static Fr fr_from_hex(const std::string& h) {
     return *v;
 }
 
+static double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+template <class T>
+static std::vector<T> read_raw(const std::string& path) {
+    std::vector<uint8_t> b = read_file(path);
+    if (b.size() % sizeof(T)) throw std::runtime_error(path + ": size is not a multiple of the element size");
+    std::vector<T> v(b.size() / sizeof(T));
+    std::memcpy(v.data(), b.data(), b.size());
+    return v;
+}
+
+// CSR (canonical coefficient words) -> iden3 .r1cs v1 in the layout r1cs_reader.rs:54-256 parses
+static int run_r1cs_write(const Args& a) {
+    const std::string prefix = a.req("prefix");
+    const uint32_t nc = (uint32_t)std::stoull(a.req("nc")), nwires = (uint32_t)std::stoull(a.req("nwires"));
+    const uint32_t ninputs = (uint32_t)std::stoull(a.req("ninputs"));
+    std::vector<uint64_t> ptr[3], val[3];
+    std::vector<uint32_t> col[3];
+    size_t cons_bytes = 0;
+    for (int k = 0; k < 3; k++) {
+        ptr[k] = read_raw<uint64_t>(prefix + "." + std::to_string(k) + ".ptr");
+        col[k] = read_raw<uint32_t>(prefix + "." + std::to_string(k) + ".col");
+        val[k] = read_raw<uint64_t>(prefix + "." + std::to_string(k) + ".val");
+        if (ptr[k].size() != (size_t)nc + 1 || ptr[k][nc] != col[k].size() || val[k].size() != col[k].size() * 4)
+            throw std::runtime_error("CSR dump " + std::to_string(k) + " is inconsistent");
+        cons_bytes += (size_t)nc * 4 + col[k].size() * 36;
+    }
+    std::vector<uint8_t> out;
+    out.reserve(12 + 3 * 12 + 64 + cons_bytes + (size_t)nwires * 8);
+    auto u32 = [&](uint32_t v) { for (int i = 0; i < 4; i++) out.push_back((uint8_t)(v >> (8 * i))); };
+    auto u64 = [&](uint64_t v) { for (int i = 0; i < 8; i++) out.push_back((uint8_t)(v >> (8 * i))); };
+    out.insert(out.end(), {'r', '1', 'c', 's'});
+    u32(1), u32(3);
+    u32(1), u64(64);  // header section
+    u32(32);
+    detail::put_le(out, detail::kFrModulus);
+    u32(nwires), u32(ninputs - 1) /* n_pub_out */, u32(0) /* n_pub_in */, u32(nwires - ninputs) /* n_prv_in */, u64(nwires), u32(nc);
+    u32(2), u64(cons_bytes);  // constraints
+    for (uint32_t i = 0; i < nc; i++)
+        for (int k = 0; k < 3; k++) {
+            u32((uint32_t)(ptr[k][i + 1] - ptr[k][i]));
+            for (uint64_t j = ptr[k][i]; j < ptr[k][i + 1]; j++) {
+                u32(col[k][j]);
+                for (int w = 0; w < 4; w++) u64(val[k][4 * j + w]);
+            }
+        }
+    u32(3), u64((uint64_t)nwires * 8);  // wire -> label map (identity)
+    for (uint32_t i = 0; i < nwires; i++) u64(i);
+    write_file(a.req("out"), out);
+    std::cout << out.size() << "\n";
+    return 0;
+}
+
+// canonical point dumps -> arkworks' uncompressed ProvingKey bytes (data_structures.rs:31-44,101-118 field order; flags as
+// ark-serialize writes them: bit 6 of a point's last byte = infinity, bit 7 = "y is the larger of {y, -y}")
+static int run_pk_write(const Args& a) {
+    const std::string prefix = a.req("prefix");
+    std::vector<uint8_t> out;
+    auto points = [&](const char* name, int words, bool with_len) {
+        std::vector<uint64_t> w = read_raw<uint64_t>(prefix + "." + name + ".bin");
+        if (w.size() % words) throw std::runtime_error(std::string(name) + ": not a whole number of points");
+        size_t n = w.size() / words;
+        if (!with_len && n != 1) throw std::runtime_error(std::string(name) + ": expected one point");
+        if (with_len)
+            for (int k = 0; k < 8; k++) out.push_back((uint8_t)((uint64_t)n >> (8 * k)));
+        size_t at = out.size();
+        out.resize(at + w.size() * 8);
+        std::memcpy(out.data() + at, w.data(), w.size() * 8);
+        for (size_t i = 0; i < n; i++) {
+            const uint64_t* p = w.data() + i * words;
+            bool inf = true;
+            for (int k = 0; k < words; k++) inf = inf && p[k] == 0;
+            uint8_t flag;
+            if (inf) flag = detail::kFlagInfinity;
+            else if (words == 8) flag = detail::fq_is_negative(Limbs{p[4], p[5], p[6], p[7]}) ? detail::kFlagNegative : 0;
+            else flag = detail::fq2_is_negative(Limbs{p[8], p[9], p[10], p[11]}, Limbs{p[12], p[13], p[14], p[15]}) ? detail::kFlagNegative : 0;
+            out[at + (i + 1) * words * 8 - 1] |= flag;
+        }
+    };
+    points("alpha_g1", 8, false), points("beta_g2", 16, false), points("gamma_g2", 16, false), points("vk_delta_g1", 8, false);
+    points("delta_g2", 16, false), points("gamma_abc_g1", 8, true), points("beta_g1", 8, false), points("delta_g1", 8, false);
+    points("a_query", 8, true), points("b_g1_query", 8, true), points("b_g2_query", 16, true), points("h_query", 8, true);
+    points("l_query", 8, true);
+    write_file(a.req("out"), out);
+    std::cout << out.size() << "\n";
+    return 0;
+}
+
+// scope row f-1: the matrices are proof-independent, so the file is parsed and flattened ONCE per circuit
+static int run_r1cs_bench(const Args& a) {
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<uint8_t> bytes = read_file(a.pos.at(0));
+    double t_file = ms_since(t0);
+    t0 = std::chrono::steady_clock::now();
+    R1CS r1cs = R1CS::from_file(R1CSFile::read(bytes));
+    double t_parse = ms_since(t0);
+    t0 = std::chrono::steady_clock::now();
+    ConstraintMatrices m = r1cs.to_matrices();
+    double t_mat = ms_since(t0);
+    printf("{\"file_bytes\": %zu, \"constraints\": %zu, \"nnz\": [%zu, %zu, %zu], \"read_file_ms\": %.1f, \"parse_ms\": %.1f, "
+           "\"to_matrices_ms\": %.1f}\n", bytes.size(), m.num_constraints, m.a_num_non_zero(), m.b_num_non_zero(), m.c_num_non_zero(),
+           t_file, t_parse, t_mat);
+    return 0;
+}
+
 template <class QAP>
 static int run_prove(const Args& a) {
+    auto t_start = std::chrono::steady_clock::now();
     auto r1cs = std::make_shared<const R1CS>(R1CS::from_file(R1CSFile::read(read_file(a.req("r1cs")))));
+    double t_r1cs = ms_since(t_start);
+    t_start = std::chrono::steady_clock::now();
     ProvingKey pk = ProvingKey::deserialize_uncompressed_unchecked(read_file(a.req("pk")));
+    double t_pk = ms_since(t_start);
     std::vector<uint8_t> wbytes = read_file(a.req("witness"));
     if (wbytes.size() != r1cs->num_variables * 32) throw std::invalid_argument("witness file must hold num_wires x 32 bytes");
     int device = std::stoi(a.get("device", "0"));
@@ -101,7 +216,7 @@ static int run_prove(const Args& a) {
     }
 
     Proof proof;
-    double ms = 0;
+    double ms = 0, first_ms = 0;
     if (shards <= 1) {
         Groth16<QAP> prover(device, precompute);
         CircomCircuit circuit{r1cs, fr_from_canonical_bulk(prover.context(), wbytes.data(), r1cs->num_variables)};
@@ -109,10 +224,13 @@ static int run_prove(const Args& a) {
             auto t0 = std::chrono::steady_clock::now();
             Proof p = prover.create_proof_with_reduction(circuit, pk, r, s);
             ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (k == 0) first_ms = ms;  // includes to_matrices, the CSR / key uploads and the window tables
             if (k && !(p == proof)) throw std::runtime_error("proof changed between repeats");
             proof = p;
         }
         fprintf(stderr, "g16_cli: %llu kernel launches, last prove %.3f ms (host clock)\n", (unsigned long long)prover.launch_count(), ms);
+        fprintf(stderr, "g16_cli timings: {\"r1cs_read_parse_ms\": %.1f, \"pk_read_deserialize_ms\": %.1f, \"first_prove_ms\": %.1f, "
+                        "\"last_prove_ms\": %.3f}\n", t_r1cs, t_pk, first_ms, ms);
     } else {
         ConstraintMatrices m = r1cs->to_matrices();
         std::vector<int> devices;
@@ -211,6 +329,9 @@ int main(int argc, char** argv) {
         Args a = parse(argc, argv, 2);
         if (cmd == "prove") return a.get("reduction", "libsnark") == "circom" ? run_prove<CircomReduction>(a) : run_prove<LibsnarkReduction>(a);
         if (cmd == "verify") return run_verify(a);
+        if (cmd == "r1cs-write") return run_r1cs_write(a);
+        if (cmd == "pk-write") return run_pk_write(a);
+        if (cmd == "r1cs-bench") return run_r1cs_bench(a);
         if (cmd == "witness-map")
             return a.get("reduction", "libsnark") == "circom" ? run_witness_map<CircomReduction>(a) : run_witness_map<LibsnarkReduction>(a);
         if (cmd == "rng" || cmd == "rand-fr") {
