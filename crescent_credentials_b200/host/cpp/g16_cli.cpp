@@ -29,9 +29,12 @@
 using namespace ark_groth16_b200;
 
 static std::vector<uint8_t> read_file(const std::string& path) {
-    std::ifstream f(path, std::ios::binary);
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
     if (!f) throw std::runtime_error("cannot open " + path);
-    return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<uint8_t> b((size_t)f.tellg());  // one sized read: the key and the .r1cs file are ~0.6 GB each
+    f.seekg(0);
+    if (!b.empty() && !f.read(reinterpret_cast<char*>(b.data()), (std::streamsize)b.size())) throw std::runtime_error("cannot read " + path);
+    return b;
 }
 static void write_file(const std::string& path, const std::vector<uint8_t>& b) {
     std::ofstream f(path, std::ios::binary);
