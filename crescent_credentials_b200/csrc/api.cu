@@ -169,6 +169,18 @@ int g16_sync(g16_ctx* ctx) {
 }
 
 // ---- device memory ----------------------------------------------------------------------------------------------------
+int g16_host_alloc(g16_ctx* ctx, size_t bytes, void** p) {
+    if (!ctx || !p) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    G16_CUDA(ctx, cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
+    return G16_OK;
+}
+int g16_host_free(g16_ctx* ctx, void* p) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (p) G16_CUDA(ctx, cudaFreeHost(p));
+    return G16_OK;
+}
 int g16_dev_alloc(g16_ctx* ctx, size_t bytes, void** p) {
     if (!ctx || !p) return G16_ERR_BAD_ARG;
     Guard g(ctx);

@@ -31,7 +31,7 @@ EXPORTS = [
     "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare", "g16_get_msm_stats", "g16_ctx_load_pk_ranges",
     "g16_prove_shard_begin_dev", "g16_prove_shard_finish_dev", "g16_copy_h_dev",
     "g16_ctx_load_vk", "g16_vk_alpha_beta", "g16_prepare_inputs", "g16_verify_batch", "g16_verify_batch_prepared",
-    "g16_verify_batch_dev", "g16_pairing",
+    "g16_verify_batch_dev", "g16_pairing", "g16_host_alloc", "g16_host_free",
 ]
 VERDICT_REJECT, VERDICT_ACCEPT, VERDICT_UNEXPECTED_IDENTITY = 0, 1, 2
 
@@ -149,6 +149,8 @@ def load_library() -> C.CDLL:
     lib.g16_r1cs_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.g16_dev_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.g16_dev_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.g16_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.g16_host_free.argtypes = [C.c_void_p, C.c_void_p]
     lib.g16_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.g16_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.g16_sync.argtypes = [C.c_void_p]
@@ -271,6 +273,15 @@ class Context:
         p = C.c_void_p()
         self.check(self.lib.g16_dev_alloc(self.h, nbytes, C.byref(p)))
         return int(p.value)
+
+    def host_alloc(self, nbytes: int) -> int:
+        """Page-locked host memory (g16_host_alloc); returns the address."""
+        p = C.c_void_p()
+        self.check(self.lib.g16_host_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def host_free(self, p: int):
+        self.check(self.lib.g16_host_free(self.h, C.c_void_p(p)))
 
     def dev_free(self, p: int):
         self.check(self.lib.g16_dev_free(self.h, C.c_void_p(p)))

@@ -702,6 +702,30 @@ class Context {
     g16_ctx* ctx_ = nullptr;
 };
 
+// A full assignment in page-locked memory (g16_host_alloc): what the witness calculator should write into, so that the per-proof
+// upload is one DMA (46 MB in 0.7 ms for rs256) instead of a driver-staged copy from pageable memory (~6 ms).
+class PinnedAssignment {
+  public:
+    PinnedAssignment(Context& ctx, size_t len) : ctx_(&ctx), len_(len) {
+        void* p = nullptr;
+        ctx.check(g16_host_alloc(ctx.get(), len * sizeof(Fr), &p), "g16_host_alloc");
+        data_ = static_cast<Fr*>(p);
+    }
+    ~PinnedAssignment() {
+        if (data_) g16_host_free(ctx_->get(), data_);
+    }
+    PinnedAssignment(const PinnedAssignment&) = delete;
+    PinnedAssignment& operator=(const PinnedAssignment&) = delete;
+    Fr* data() { return data_; }
+    const Fr* data() const { return data_; }
+    size_t size() const { return len_; }
+
+  private:
+    Context* ctx_;
+    Fr* data_ = nullptr;
+    size_t len_;
+};
+
 // ---- Groth16<Bn254, QAP> prover bound to one GPU ---------------------------------------------------------------------------------------------
 // The reference keeps nothing between calls; here an opaque persistent context owns the device copies of the proving key
 // queries and of the CSR matrices, keyed by object identity, loaded lazily on first use (SURVEY 8b "Ownership").
@@ -735,6 +759,20 @@ class Groth16 {
         ctx_.check(g16_prove(ctx_.get(), words(full_assignment), r.v.data(), s.v.data(), QAP::ID, &out), "g16_prove");
         return Proof::from_abi(out);
     }
+
+    // same call with the assignment in caller-owned memory (e.g. a PinnedAssignment)
+    Proof create_proof_with_reduction_and_matrices(const ProvingKey& pk, const Fr& r, const Fr& s, const ConstraintMatrices& matrices,
+                                                   size_t num_inputs, size_t num_constraints, const Fr* full_assignment, size_t len) {
+        std::lock_guard<std::mutex> g(mu_);
+        ensure_matrices(matrices, num_inputs, num_constraints);
+        ensure_pk(pk);
+        check_assignment(matrices, len);
+        g16_proof out{};
+        ctx_.check(g16_prove(ctx_.get(), reinterpret_cast<const uint64_t*>(full_assignment), r.v.data(), s.v.data(), QAP::ID, &out), "g16_prove");
+        return Proof::from_abi(out);
+    }
+    // the matrices of a circuit's R1CS, built once and cached
+    const ConstraintMatrices& matrices_of(const std::shared_ptr<const R1CS>& r1cs) { return matrices_for(r1cs); }
 
     // prover.rs:177-221: the circuit owns the R1CS and the witness.  The matrices are proof-independent, so they are built
     // from the circuit's R1CS once and cached instead of re-synthesised per proof.

@@ -4,7 +4,7 @@
 // prover_params.bin, take the witness, prove, write the proof -- nothing else of the CLI (no JWT handling, no show/verify).
 //
 //   g16_cli prove --r1cs F --pk F --witness F (--r HEX --s HEX | --seed N | --test-rng | --no-zk) [--reduction circom]
-//                 [--no-precompute] [--shards K] [--device D] [--repeat N] --out F
+//                 [--no-precompute] [--shards K] [--device D] [--repeat N] [--pageable] --out F
 //   g16_cli witness-map --r1cs F --witness F [--reduction circom] --out F      (n x 32 bytes, canonical little-endian)
 //   g16_cli rng (test | seed:N) COUNT          next_u64 draws of StdRng, one hex word per line
 //   g16_cli rand-fr (test | seed:N) COUNT      Fr::rand draws, canonical value as hex
@@ -64,7 +64,7 @@ struct Args {
     }
 };
 static Args parse(int argc, char** argv, int from) {
-    static const char* flags[] = {"test-rng", "no-zk", "no-precompute"};
+    static const char* flags[] = {"test-rng", "no-zk", "no-precompute", "pageable"};
     Args a;
     for (int i = from; i < argc; i++) {
         std::string s = argv[i];
@@ -223,9 +223,22 @@ static int run_prove(const Args& a) {
     if (shards <= 1) {
         Groth16<QAP> prover(device, precompute);
         CircomCircuit circuit{r1cs, fr_from_canonical_bulk(prover.context(), wbytes.data(), r1cs->num_variables)};
+        // by default the assignment lives in page-locked memory (what a witness calculator bound to this library would fill);
+        // --pageable proves straight from the std::vector of the CircomCircuit
+        std::unique_ptr<PinnedAssignment> pinned;
+        if (!a.has("pageable")) {
+            pinned = std::make_unique<PinnedAssignment>(prover.context(), circuit.witness->size());
+            std::memcpy(pinned->data(), circuit.witness->data(), circuit.witness->size() * sizeof(Fr));
+        }
         for (int k = 0; k < repeat; k++) {
             auto t0 = std::chrono::steady_clock::now();
-            Proof p = prover.create_proof_with_reduction(circuit, pk, r, s);
+            Proof p;
+            if (pinned) {
+                const ConstraintMatrices& m = prover.matrices_of(circuit.r1cs);
+                p = prover.create_proof_with_reduction_and_matrices(pk, r, s, m, m.num_instance_variables, m.num_constraints, pinned->data(),
+                                                                    pinned->size());
+            } else
+                p = prover.create_proof_with_reduction(circuit, pk, r, s);
             ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (k == 0) first_ms = ms;  // includes to_matrices, the CSR / key uploads and the window tables
             if (k && !(p == proof)) throw std::runtime_error("proof changed between repeats");

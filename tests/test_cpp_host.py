@@ -188,7 +188,7 @@ def test_cpp_prove_matches_golden(cli, tmp_path, name, precompute):
     if meta["reduction"] == "circom":
         args += ["--reduction", "circom"]
     if not precompute:
-        args.append("--no-precompute")
+        args += ["--no-precompute", "--pageable"]  # the witness straight from the CircomCircuit's std::vector (default: page-locked copy)
     out = cli(*args)
     assert out.stdout.strip() == meta["proof_compressed"]
     assert (tmp_path / "proof.bin").read_bytes().hex() == meta["proof_uncompressed"]

@@ -99,6 +99,12 @@ def main():
         if line.startswith("g16_cli timings:"):
             out["cli_timings_ms"] = json.loads(line.split(":", 1)[1])
     out["cli_proof_equals_python_proof"] = p.stdout.strip() == p1.serialize_compressed().hex()
+    p_pg = run("prove", "--r1cs", r1cs_path, "--pk", pk_path, "--witness", os.path.join(tmp, "z.bin"), "--r", hex(r), "--s", hex(s),
+               "--out", os.path.join(tmp, "proof_pg.bin"), "--repeat", 3, "--pageable")
+    for line in p_pg.stderr.splitlines():
+        if line.startswith("g16_cli timings:"):
+            out["cli_timings_pageable_ms"] = json.loads(line.split(":", 1)[1])
+    out["cli_pageable_proof_equals"] = p_pg.stdout.strip() == p.stdout.strip()
     out["cli_proof_file_equals"] = open(os.path.join(tmp, "proof.bin"), "rb").read() == p1.serialize_uncompressed()
 
     # ---- f-4 at full size -------------------------------------------------------------------------------------------------------
