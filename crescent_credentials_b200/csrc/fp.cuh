@@ -27,6 +27,17 @@
 #define G16_HD_NOINLINE inline
 #endif
 
+// The Montgomery product is ~180 straight-line instructions (2.9 KB of SASS).  The pairing of verify.cu holds ~260 inlined
+// copies and runs with 2 warps per scheduler; ncu shows stall_no_instruction 1.8 per issue at saturation.  A translation unit
+// may define G16_MUL_AS_CALL before including this header to make the product ONE shared function instead (verify.cu does
+// with -DG16_VERIFY_MUL_CALL): 147 k -> 94 k SASS instructions, but MEASURED SLOWER (754 k vs 807 k proofs/s, 26.9 vs 23.0 ms
+// for one proof): the call sequence costs more than the fetch stalls it removes.  Kept as a switch for the record.
+#ifdef G16_MUL_AS_CALL
+#define G16_MUL_ATTR G16_HD_NOINLINE
+#else
+#define G16_MUL_ATTR G16_HD
+#endif
+
 namespace g16 {
 
 struct limbs8 {
@@ -429,7 +440,7 @@ struct alignas(16) Fp {
     // 132 IADD3 + 44 SEL/LOP3): measured SLOWER on B200 (56.2 vs 64.9 G mul/s, bucket loop 8.5 vs 6.3 ms) because the
     // extra ALU work and code size cost more than the 10 % of wide multiplies they save.  Kept for the record and
     // because reduce_wide is the building block for sharing reductions between products.
-    friend G16_HD Fp operator*(const Fp& a, const Fp& b) {
+    friend G16_MUL_ATTR Fp operator*(const Fp& a, const Fp& b) {
 #ifdef G16_MUL_KARATSUBA
         uint32_t P[16];
         mul8_wide(P, a.v, b.v);

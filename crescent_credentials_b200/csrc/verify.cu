@@ -12,6 +12,9 @@
 // step ~30) + 27 x (3 x 39 + addition step ~40) ~ 17.6 k; final exponentiation ~ 3 x (62 x 18 + 27 x 54) + ~1 k ~ 8.7 k;
 // prepare_inputs 32 x 10 per public input.  No HBM traffic to speak of: the kernels are bound by the multiplier pipe and,
 // at small batch sizes, by the latency of one thread's dependent chain.
+#ifdef G16_VERIFY_MUL_CALL
+#define G16_MUL_AS_CALL  // fp.cuh: the Montgomery product as one shared function for this translation unit
+#endif
 #include "internal.cuh"
 #include "pairing.cuh"
 
