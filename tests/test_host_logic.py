@@ -262,3 +262,34 @@ def test_cpu_sample_scaling_follows_arkworks_window_rule():
     # a 12.5 % sample pays more additions per point than the full MSM: the scale factor stays below len/sample
     k = full // 8
     assert 1.0 < bench.cpu_scale(full, k, 16) < full / k
+
+
+def test_vectorised_r1cs_loader_equals_the_rowwise_definition():
+    """Ragged rows, empty rows, repeated wires (summing to non-zero and to zero), explicit zero coefficients, unsorted wires,
+    an unreduced coefficient: the array-based loader must produce exactly the CSR of the term-by-term one."""
+    from crescent_credentials_b200.r1cs import _load_matrices_rowwise
+    import random
+    rnd = random.Random(4242)
+    nw, nc = 37, 60
+    cons = []
+    for i in range(nc):
+        row = []
+        for k in range(3):
+            n = rnd.choice([0, 0, 1, 2, 3, 5, 9])
+            lc = [(rnd.randrange(nw), rnd.choice([1, o.R_MOD - 1, rnd.randrange(o.R_MOD), 0 if rnd.random() < 0.1 else 7])) for _ in range(n)]
+            if lc and rnd.random() < 0.2:
+                w, v = lc[0]
+                lc.append((w, (o.R_MOD - v) % o.R_MOD if rnd.random() < 0.5 else 3))  # repeat a wire: cancels or sums
+            rnd.shuffle(lc)
+            row.append(lc)
+        cons.append(tuple(row))
+    data = bytearray(o.write_r1cs(nw, 2, 1, nw - 4, cons))
+    a, b = load_matrices(bytes(data)), _load_matrices_rowwise(bytes(data))
+    for k in range(3):
+        assert np.array_equal(a.row_ptr[k], b.row_ptr[k]) and np.array_equal(a.col[k], b.col[k]) and np.array_equal(a.val[k], b.val[k])
+    assert (a.num_instance_variables, a.num_witness_variables, a.num_constraints) == (b.num_instance_variables, b.num_witness_variables, nc)
+    for name in ("rand300", "dummy924_nozk", "silly"):
+        _, r1cs_bytes, _ = load_golden(name)
+        a, b = load_matrices(r1cs_bytes), _load_matrices_rowwise(r1cs_bytes)
+        for k in range(3):
+            assert np.array_equal(a.row_ptr[k], b.row_ptr[k]) and np.array_equal(a.col[k], b.col[k]) and np.array_equal(a.val[k], b.val[k])
