@@ -53,8 +53,18 @@ G16_HD Fq pc_fq(int i) {
 }
 G16_HD Fq2 pc_fq2(int i) { return Fq2{pc_fq(i), pc_fq(i + 1)}; }
 
+// Code-size switch for the verifier kernels (ncu: stall_no_instruction 1.8 per issue at saturation): with G16_PAIRING_COMPACT the
+// small helpers that are inlined at many call sites (the xi multiplication: 10 field additions; the line evaluation: 4 products)
+// become single functions: 147 k -> 101 k SASS instructions in verify.o, but MEASURED SLOWER (741 k vs 809 k proofs/s at 65 536
+// proofs; single proof 22.6 vs 22.5 ms) -- ptxas schedules better across the inlined helpers than the fetch stalls cost.  Off.
+#ifdef G16_PAIRING_COMPACT
+#define G16_PAIRING_HELPER G16_HD_NOINLINE
+#else
+#define G16_PAIRING_HELPER G16_HD
+#endif
+
 // ---- Fq2 helpers -------------------------------------------------------------------------------------------------------------
-G16_HD Fq2 fq2_mul_xi(const Fq2& a) {  // (9 + u)(a0 + a1 u) = (9 a0 - a1) + (9 a1 + a0) u
+G16_PAIRING_HELPER Fq2 fq2_mul_xi(const Fq2& a) {  // (9 + u)(a0 + a1 u) = (9 a0 - a1) + (9 a1 + a0) u
     Fq t0 = a.c0.dbl().dbl().dbl() + a.c0;
     Fq t1 = a.c1.dbl().dbl().dbl() + a.c1;
     return Fq2{t0 - a.c1, t1 + a.c0};
@@ -222,7 +232,7 @@ G16_HD G2Affine g2_mul_by_char(const G2Affine& q) {
 }
 
 // f *= line(P)   (Bn::ell, TwistType::D)
-G16_HD void ell(Fq12& f, const EllCoeff& c, const G1Affine& p) { f.mul_by_034(fq2_mul_fq(c.c0, p.y), fq2_mul_fq(c.c1, p.x), c.c2); }
+G16_PAIRING_HELPER void ell(Fq12& f, const EllCoeff& c, const G1Affine& p) { f.mul_by_034(fq2_mul_fq(c.c0, p.y), fq2_mul_fq(c.c1, p.x), c.c2); }
 
 G16_HD int ate_digit(int i) { return (int)((G16_ATE_POS >> i) & 1ull) - (int)((G16_ATE_NEG >> i) & 1ull); }
 
