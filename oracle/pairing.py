@@ -17,9 +17,13 @@ forks/groth16/Cargo.toml:18-24, no lockfile in the tree).  Its published algorit
   * final_exponentiation: easy part (q^6-1)(q^2+1), hard part after Fuentes-Castaneda et al. ("Faster hashing to G2"):
     the result is  f^(2x(6x^2+3x+1) * (q^4-q^2+1)/r)  -- a fixed power of the reduced Tate pairing; this module checks that
     identity numerically (hard_part_exponent) so the restated addition chain is pinned to the published exponent.
-ASSUMPTION (cannot be checked against an arkworks binary in this container): the digit string ATE_LOOP_COUNT, the order of
-the line multiplications inside one step and the hard-part chain are as published in ark-ec 0.4 / ark-bn254 0.4.  None of
-them changes a verification verdict; they only fix the bytes of GT elements such as PreparedVerifyingKey.alpha_g1_beta_g2.
+PINNED against the reference tree's own second BN254 implementation (forks/halo2curves/src/bn256, same tower; fixture
+tests/golden/halo2curves_bn256_pins.json): the BN parameter x, the 65 signed digits of 6x+2 (mod.rs:17-24), the Frobenius
+coefficients xi^((q^n-1)/6), xi^((q^n-1)/3), xi^(2(q^n-1)/3) (fq12.rs:40-, fq6.rs:46-,126-) and xi^((q-1)/2) (engine.rs:164-177);
+the Frobenius-addition step Q1 = (conj(x) xi^((q-1)/3), conj(y) xi^((q-1)/2)), -Q2 = (x xi^((q^2-1)/3), y) is the one at
+engine.rs:179-193.  ASSUMPTION (cannot be checked against an arkworks binary in this container): that ark-bn254 0.4 uses this same
+digit string and that the hard-part chain is the one published in ark-ec 0.4 (its exponent is checked numerically below).  None of
+this changes a verification verdict; it only fixes the bytes of GT elements such as PreparedVerifyingKey.alpha_g1_beta_g2.
 
 Here Fq12 is handled as Fq2[w]/(w^6 - xi) (six Fq2 coefficients), deliberately NOT the tower the CUDA code uses
 (Karatsuba over Fq6): the two only share the mathematics.  to_tower / from_tower convert to ark-serialize's coefficient order.

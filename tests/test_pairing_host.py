@@ -317,3 +317,45 @@ def test_device_pairing_on_host_equals_cpp_oracle_on_random_points(hp):
         hp.host_miller3(p3.ctypes.data_as(ctypes.c_void_p), act, Qm[i].ctypes.data_as(ctypes.c_void_p), zero_tab, zero_tab, f)
         assert hp.host_final_exp(f, out) == 1
         assert out.raw == want[i].tobytes(), i
+
+
+def test_pairing_constants_pinned_to_the_reference_trees_halo2curves_copy():
+    """The reference tree carries a second BN254 implementation (forks/halo2curves, same tower): its BN parameter, the signed
+    digits of 6x+2, its Frobenius coefficients and twist constants (tests/golden/halo2curves_bn256_pins.json, extracted by
+    make_halo2curves_pins.py) must equal what the oracle derives from q and xi -- and the Montgomery limbs the device code
+    is compiled with (csrc/pairing_consts.inc) must be those very words."""
+    with open(os.path.join(GOLDEN, "halo2curves_bn256_pins.json")) as f:
+        pins = json.load(f)
+
+    def fq2(l):
+        v = [int(x, 16) for x in l]
+        return (o.from_mont(sum(v[i] << (64 * i) for i in range(4)), Q), o.from_mont(sum(v[4 + i] << (64 * i) for i in range(4)), Q))
+
+    assert pins["BN_X"] == P.BN_X
+    assert pins["SIX_U_PLUS_2_NAF"] == P.ATE_LOOP_COUNT
+    for n in (1, 2, 3):
+        assert fq2(pins["FROBENIUS_COEFF_FQ12_C1"][n]) == P._FROB[n][1]     # xi^((q^n - 1)/6)
+        assert fq2(pins["FROBENIUS_COEFF_FQ6_C1"][n]) == P._FROB[n][2]      # xi^((q^n - 1)/3)
+        assert fq2(pins["FROBENIUS_COEFF_FQ6_C2"][n]) == P._FROB[n][4]      # xi^(2 (q^n - 1)/3)
+    assert fq2(pins["FROBENIUS_COEFF_FQ12_C1"][0]) == (1, 0)
+    assert fq2(pins["XI_TO_Q_MINUS_1_OVER_2"]) == P.TWIST_MUL_BY_Q_Y
+    assert fq2(pins["FROBENIUS_COEFF_FQ6_C1"][1]) == P.TWIST_MUL_BY_Q_X
+    # the same words in the generated include: 8 x u32 per Fq, c0 then c1
+    text = open(os.path.join(ROOT, "crescent_credentials_b200", "csrc", "pairing_consts.inc")).read()
+
+    def inc_rows(l):
+        v = [int(x, 16) for x in l]
+        rows = []
+        for half in (v[:4], v[4:]):
+            limbs32 = []
+            for w in half:
+                limbs32 += [w & 0xFFFFFFFF, w >> 32]
+            rows.append(", ".join("0x%08xu" % x for x in limbs32))
+        return rows
+
+    for key, idx in (("FROBENIUS_COEFF_FQ12_C1", 1), ("FROBENIUS_COEFF_FQ12_C1", 2), ("FROBENIUS_COEFF_FQ12_C1", 3),
+                     ("FROBENIUS_COEFF_FQ6_C1", 1), ("FROBENIUS_COEFF_FQ6_C2", 1)):
+        for row in inc_rows(pins[key][idx]):
+            assert row in text, (key, idx)
+    for row in inc_rows(pins["XI_TO_Q_MINUS_1_OVER_2"]):
+        assert row in text
