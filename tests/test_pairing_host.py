@@ -359,3 +359,44 @@ def test_pairing_constants_pinned_to_the_reference_trees_halo2curves_copy():
             assert row in text, (key, idx)
     for row in inc_rows(pins["XI_TO_Q_MINUS_1_OVER_2"]):
         assert row in text
+
+
+def test_oracle_gt_is_a_fixed_power_of_the_in_tree_halo2curves_gt():
+    """The reference tree's halo2curves copy raises the Miller value to (q^12 - 1)/r exactly (the Devegili / Scott chain of
+    forks/halo2curves/src/bn256/engine.rs:24-117, restated below); ark-ec's hard part raises it to 2x(6x^2+3x+1) times that.
+    So for the same Miller value:  GT_arkworks-shape == GT_halo2curves-shape ^ (2x(6x^2+3x+1)),  and both have order r."""
+    def exp_by_x(f):
+        return P.f12_pow(f, P.BN_X)
+
+    def halo2curves_final_exponentiation(f):
+        r = P.f12_mul(P.f12_conj(f), P.f12_inv(f))
+        r = P.f12_mul(P.f12_frobenius(r, 2), r)
+        fp, fp2 = P.f12_frobenius(r, 1), P.f12_frobenius(r, 2)
+        fp3 = P.f12_frobenius(fp2, 1)
+        fu = exp_by_x(r)
+        fu2 = exp_by_x(fu)
+        fu3 = exp_by_x(fu2)
+        y3 = P.f12_conj(P.f12_frobenius(fu, 1))
+        fu2p, fu3p = P.f12_frobenius(fu2, 1), P.f12_frobenius(fu3, 1)
+        y2 = P.f12_frobenius(fu2, 2)
+        y0 = P.f12_mul(P.f12_mul(fp, fp2), fp3)
+        y1 = P.f12_conj(r)
+        y5 = P.f12_conj(fu2)
+        y4 = P.f12_conj(P.f12_mul(fu, fu2p))
+        y6 = P.f12_conj(P.f12_mul(fu3, fu3p))
+        y6 = P.f12_mul(P.f12_mul(P.f12_sqr(y6), y4), y5)
+        t1 = P.f12_mul(P.f12_mul(y3, y5), y6)
+        y6 = P.f12_mul(y6, y2)
+        t1 = P.f12_sqr(P.f12_mul(P.f12_sqr(t1), y6))
+        t0 = P.f12_mul(t1, y1)
+        t1 = P.f12_mul(t1, y0)
+        return P.f12_mul(P.f12_sqr(t0), t1)
+
+    x = P.BN_X
+    mult = 2 * x * (6 * x * x + 3 * x + 1)
+    for a, b in ((1, 1), (o.stream_fr(0xAB, 1), o.stream_fr(0xAB, 2))):
+        f = P.multi_miller_loop([o.G1.mul(o.G1_GEN, a)], [o.G2.mul(o.G2_GEN, b)])
+        h = halo2curves_final_exponentiation(f)
+        assert h == P.f12_pow(f, (Q**12 - 1) // o.R_MOD)                     # the exact reduced pairing
+        assert P.final_exponentiation(f) == P.f12_pow(h, mult)
+        assert h != P.F12_ONE and P.f12_pow(h, o.R_MOD) == P.F12_ONE
