@@ -399,6 +399,68 @@ struct alignas(16) Fp {
         reduce_once(r.v, cy);
         return r;
     }
+    // Three independent Montgomery products in lock-step: row i of every product before row i + 1, so that the six carry chains
+    // (two per product) sit next to each other in the instruction stream.  ptxas keeps the rows of ONE product in order (each
+    // is an asm block with a carry chain) and, given three separate mul_cios calls, emits the products one after the other;
+    // written this way a thread has three times as many independent IMAD.WIDE chains in flight.  Same arithmetic, same result
+    // bits as three mul_cios calls.  Used by Fq2::operator* when G16_FQ2_MUL3 is defined (off by default: prepared at the end
+    // of round 1, checked on the host against the oracle, not yet measured on the GPU).
+    static G16_HD void mul_cios3(const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, const Fp& a2, const Fp& b2, Fp& r0, Fp& r1,
+                                 Fp& r2) {
+        uint32_t A[3][8], B[3][8];  // operand copies: fully unrolled below, so these live in registers
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            A[0][k] = a0.v[k], A[1][k] = a1.v[k], A[2][k] = a2.v[k];
+            B[0][k] = b0.v[k], B[1][k] = b1.v[k], B[2][k] = b2.v[k];
+        }
+        uint32_t X[3][8], Y[3][8];
+        uint32_t m[3], cy[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            lanes_mul(X[j], A[j][0], A[j][2], A[j][4], A[j][6], B[j][0]);
+            lanes_mul(Y[j], A[j][1], A[j][3], A[j][5], A[j][7], B[j][0]);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            m[j] = X[j][0] * PR::INV;
+            lanes_mad(Y[j], PR::P(1), PR::P(3), PR::P(5), PR::P(7), m[j]);
+            cy[j] = lanes_mad(X[j], PR::P(0), PR::P(2), PR::P(4), PR::P(6), m[j]);
+            Y[j][7] += cy[j];
+        }
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                uint32_t* ev = (i & 1) ? Y[j] : X[j];
+                uint32_t* od = (i & 1) ? X[j] : Y[j];
+                lanes_fold_shift_mad(ev[0], od, A[j][1], A[j][3], A[j][5], A[j][7], B[j][i]);
+                cy[j] = lanes_mad(ev, A[j][0], A[j][2], A[j][4], A[j][6], B[j][i]);
+                od[7] += cy[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                uint32_t* ev = (i & 1) ? Y[j] : X[j];
+                uint32_t* od = (i & 1) ? X[j] : Y[j];
+                m[j] = ev[0] * PR::INV;
+                lanes_mad(od, PR::P(1), PR::P(3), PR::P(5), PR::P(7), m[j]);
+                cy[j] = lanes_mad(ev, PR::P(0), PR::P(2), PR::P(4), PR::P(6), m[j]);
+                od[7] += cy[j];
+            }
+        }
+        Fp out[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            uint32_t sh[8];
+#pragma unroll
+            for (int k = 0; k < 7; k++) sh[k] = Y[j][k + 1];
+            sh[7] = 0;
+            uint32_t c = add8(out[j].v, sh, X[j]);
+            reduce_once(out[j].v, c);
+        }
+        r0 = out[0];
+        r1 = out[1];
+        r2 = out[2];
+    }
     // Montgomery reduction of a 16-limb value P < p * 2^256:  P * 2^-256 mod p, fully reduced.
     // Same two-accumulator scheme as mul_cios with the product rows removed: the high limbs of P enter one per round
     // at the top of the accumulator.
@@ -571,9 +633,14 @@ struct Fq2 {
     // loop is 28 Fq products (~110 KB of SASS), overflows the instruction cache (ncu: stall_no_instruction second
     // largest) and needs 255 registers; as calls it runs 12 % faster at 168 registers (profiles/r01_notes.md).
     friend G16_HD_NOINLINE Fq2 operator*(const Fq2& a, const Fq2& b) {
+#ifdef G16_FQ2_MUL3
+        Fq v0, v1, s;  // the three products in lock-step (mul_cios3): six carry chains in flight instead of two
+        Fq::mul_cios3(a.c0, b.c0, a.c1, b.c1, a.c0 + a.c1, b.c0 + b.c1, v0, v1, s);
+#else
         Fq v0 = a.c0 * b.c0;
         Fq v1 = a.c1 * b.c1;
         Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
+#endif
         return Fq2{v0 - v1, s - v0 - v1};
     }
     // complex squaring: 2 Fq multiplications

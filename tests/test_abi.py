@@ -107,6 +107,36 @@ def test_device_fq2_code_on_host_matches_oracle(host_fp):
         assert dec(_call(host_fp.host_fq2_op, 4, enc(a), enc(b), 64)) == o.Fq2.inv(a)
 
 
+def test_lockstep_triple_product_on_host_matches_oracle():
+    """fp.cuh mul_cios3 (three Montgomery products row-interleaved; Fq2 products use it under -DG16_FQ2_MUL3, off by default):
+    the host build with the switch on must give the oracle's Fq2 products, and the whole pairing built on it the oracle's GT."""
+    import random
+    import pairing as P
+    out = os.path.join(ROOT, "tests", "_host_fp_mul3.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DG16_FQ2_MUL3", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "host_fp_shim.cpp")])
+    lib = ctypes.CDLL(out)
+    rnd = random.Random(33)
+    enc = lambda v: o.mont_le_bytes(v[0], o.Q_MOD) + o.mont_le_bytes(v[1], o.Q_MOD)
+    dec = lambda b: (o.from_mont(int.from_bytes(b[:32], "little"), o.Q_MOD), o.from_mont(int.from_bytes(b[32:], "little"), o.Q_MOD))
+    edge = [0, 1, o.Q_MOD - 1, (o.Q_MOD - 1) // 2]
+    cases = [((x, y), (y, x)) for x in edge for y in edge] + [((rnd.randrange(o.Q_MOD), rnd.randrange(o.Q_MOD)),
+                                                               (rnd.randrange(o.Q_MOD), rnd.randrange(o.Q_MOD))) for _ in range(40)]
+    for a, b in cases:
+        assert dec(_call(lib.host_fq2_op, 0, enc(a), enc(b), 64)) == o.Fq2.mul(a, b)
+    outp = os.path.join(ROOT, "tests", "_host_pairing_mul3.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DG16_FQ2_MUL3", "-shared", "-fPIC", "-o", outp, os.path.join(ROOT, "tests", "host_pairing_shim.cpp")])
+    hp = ctypes.CDLL(outp)
+    from test_pairing_host import enc_g1, enc_g2, dec_f12
+    p, q = o.G1.mul(o.G1_GEN, o.stream_fr(0x3A, 1)), o.G2.mul(o.G2_GEN, o.stream_fr(0x3A, 2))
+    act = (ctypes.c_int * 3)(1, 0, 0)
+    zero = ctypes.create_string_buffer(91 * 192)
+    f, gt = ctypes.create_string_buffer(384), ctypes.create_string_buffer(384)
+    pts = enc_g1(p) + bytes(128)
+    hp.host_miller3(ctypes.create_string_buffer(pts, len(pts)), act, ctypes.create_string_buffer(enc_g2(q), 128), zero, zero, f)
+    assert hp.host_final_exp(f, gt) == 1
+    assert dec_f12(gt.raw) == P.pairing(p, q)
+
+
 def test_serialisation_mirror_matches_oracle():
     rnd = random.Random(9)
     for _ in range(20):
