@@ -917,6 +917,12 @@ class Groth16Verifier {
         return verify_proofs(pvk, {proof}, {public_inputs})[0];
     }
 
+    // SNARK trait names (forks/groth16/src/lib.rs:84-96)
+    PreparedVerifyingKey process_vk(const VerifyingKey& circuit_vk, int encoding) { return prepare_verifying_key(circuit_vk, encoding); }
+    bool verify_with_processed_vk(const PreparedVerifyingKey& circuit_pvk, const std::vector<Fr>& x, const Proof& proof) {
+        return verify_proof(circuit_pvk, proof, x);
+    }
+
     // n independent verify_proof calls in one launch
     std::vector<bool> verify_proofs(const PreparedVerifyingKey& pvk, const std::vector<Proof>& proofs,
                                     const std::vector<std::vector<Fr>>& public_inputs) {

@@ -145,6 +145,17 @@ class Verifier:
     def verify_proof(self, pvk: PreparedVerifyingKey, proof: Proof, public_inputs: Sequence[int]) -> bool:
         return self.verify_proofs(pvk, [proof], [public_inputs])[0]
 
+    # -- SNARK trait names (forks/groth16/src/lib.rs:84-96) ---------------------------------------------------------------------
+    def process_vk(self, circuit_vk) -> PreparedVerifyingKey:
+        return self.prepare_verifying_key(circuit_vk)
+
+    def verify_with_processed_vk(self, circuit_pvk: PreparedVerifyingKey, x: Sequence[int], proof: Proof) -> bool:
+        return self.verify_proof(circuit_pvk, proof, x)
+
+    def verify(self, vk, x: Sequence[int], proof: Proof) -> bool:
+        """SNARK::verify: process_vk + verify_with_processed_vk."""
+        return self.verify_with_processed_vk(self.process_vk(vk), x, proof)
+
     # -- the batched form: n independent verify_proof calls in one launch ------------------------------------------------------
     def verify_proofs(self, pvk: PreparedVerifyingKey, proofs: Sequence[Proof], public_inputs: Sequence[Sequence[int]]) -> List[bool]:
         if len(proofs) != len(public_inputs):

@@ -87,6 +87,7 @@ def test_verify_golden_proofs_and_tampered_ones(name):
         assert ver.verify_proof_with_prepared_inputs(pvk, g.Proof(A, B, C), pi) is True
         assert ver.verify_proof_with_prepared_inputs(pvk, g.Proof(A, B, C), o.G1.add(pi, o.G1_GEN)) is False
         assert ver.verify_proofs(pvk, [], []) == []
+        assert ver.verify_with_processed_vk(pvk, inputs, g.Proof(A, B, C)) is True  # SNARK trait spelling (lib.rs:89-96)
         with pytest.raises(v.MalformedVerifyingKey):
             ver.verify_proof(pvk, g.Proof(A, B, C), list(inputs) + [7])
     finally:
