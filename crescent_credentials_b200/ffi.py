@@ -189,6 +189,9 @@ class Context:
             raise G16Error(rc, self.lib.g16_last_error(None).decode())
         self.h = h
         self.device = device
+        self.vk_inputs = None
+        self.vk_generation = 0   # bumped by every load_vk: lets several Verifiers share one context safely
+        self._wires = None       # num_wires of the loaded R1CS (size checks of z)
 
     def close(self):
         if getattr(self, "h", None):
@@ -307,7 +310,9 @@ class Context:
             v.row_ptr[k] = C.cast(rp.ctypes.data, _u64p)
             v.col[k] = C.cast(cc.ctypes.data, _u32p)
             v.val[k] = C.cast(vv.ctypes.data, _u64p)
+        self._wires = None
         self.check(self.lib.g16_ctx_load_r1cs(self.h, C.byref(v)))
+        self._wires = int(m)
 
     def load_pk(self, arrays: dict, encoding=ENC_MONTGOMERY, shard_rank=0, shard_count=1, precompute=False,
                 h_range=None, z_range=None):
@@ -339,8 +344,18 @@ class Context:
         self.check(self.lib.g16_domain_size(self.h, C.byref(n)))
         return int(n.value)
 
+    def _check_z(self, z):
+        """A numpy witness must hold exactly num_wires x 4 words (the C side copies m * 32 bytes from the pointer)."""
+        if isinstance(z, np.ndarray) and self._wires is not None and z.size != self._wires * 4:
+            raise G16Error(ERR_BAD_ARG, f"witness holds {z.size} words, the loaded R1CS has {self._wires} wires x 4")
+
+    def _check_words(self, what: str, a, words: int):
+        if isinstance(a, np.ndarray) and a.size * a.itemsize != words * 8:
+            raise G16Error(ERR_BAD_ARG, f"{what}: buffer of {a.size * a.itemsize} bytes, expected {words * 8}")
+
     def witness_map(self, z: np.ndarray, reduction=REDUCTION_LIBSNARK) -> np.ndarray:
         z = np.ascontiguousarray(z, dtype=np.uint64)
+        self._check_z(z)
         n = self.domain_size()
         h = np.empty((n, 4), dtype=np.uint64)
         got = C.c_size_t(0)
@@ -357,6 +372,7 @@ class Context:
         """z: numpy (m x 4 uint64) or a raw host address (e.g. pinned memory) of m Montgomery elements."""
         if isinstance(z, np.ndarray):
             z = np.ascontiguousarray(z, dtype=np.uint64)
+            self._check_z(z)
         r = np.ascontiguousarray(r, dtype=np.uint64)
         s = np.ascontiguousarray(s, dtype=np.uint64)
         out = ProofOut()
@@ -366,6 +382,7 @@ class Context:
     def upload_witness(self, z):
         if isinstance(z, np.ndarray):
             z = np.ascontiguousarray(z, dtype=np.uint64)
+            self._check_z(z)
         self.check(self.lib.g16_upload_witness(self.h, _ptr(z)))
 
     def prove_resident(self, r, s, reduction=REDUCTION_LIBSNARK) -> ProofOut:
@@ -449,8 +466,22 @@ class Context:
         v.gamma_abc_g1 = abc.ctypes.data_as(_u64p)
         v.gamma_abc_len = abc.shape[0]
         v.encoding = encoding
+        self.vk_inputs = None
+        self.vk_generation += 1
         self.check(self.lib.g16_ctx_load_vk(self.h, C.byref(v)))
         self.vk_inputs = abc.shape[0] - 1
+
+    def _check_vk_args(self, proofs, inputs, n: int):
+        """Sizes of the host buffers of the verify calls against n and the loaded key (the C side reads n * 272 proof bytes
+        and n * vk_inputs * 32 input bytes from the raw pointers)."""
+        if self.vk_inputs is None:
+            raise G16Error(ERR_BAD_ARG, "no verifying key loaded")
+        if proofs is not None:
+            have = proofs.size * proofs.itemsize if isinstance(proofs, np.ndarray) else C.sizeof(proofs)
+            if have != n * C.sizeof(ProofOut):
+                raise G16Error(ERR_BAD_ARG, f"proofs buffer of {have} bytes, expected {n} x {C.sizeof(ProofOut)}")
+        if inputs is not None:
+            self._check_words("public inputs", inputs, n * self.vk_inputs * 4)
 
     def vk_alpha_beta(self) -> np.ndarray:
         out = np.zeros(48, dtype=np.uint64)
@@ -459,6 +490,7 @@ class Context:
 
     def prepare_inputs(self, public_inputs: np.ndarray, n: int) -> np.ndarray:
         x = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+        self._check_vk_args(None, x, n)
         out = np.zeros((n, 8), dtype=np.uint64)
         self.check(self.lib.g16_prepare_inputs(self.h, _ptr(x) if x.size else None, n, _ptr(out)))
         return out
@@ -466,6 +498,7 @@ class Context:
     def verify_batch(self, proofs, public_inputs: np.ndarray, n: int) -> np.ndarray:
         """proofs: ctypes array of ProofOut (g16_proof) or a uint8 numpy buffer of n * 272 bytes."""
         x = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+        self._check_vk_args(proofs, x, n)
         out = np.zeros(n, dtype=np.uint8)
         pp = _ptr(proofs) if isinstance(proofs, np.ndarray) else C.cast(proofs, C.c_void_p)
         self.check(self.lib.g16_verify_batch(self.h, pp, _ptr(x) if x.size else None, n, _ptr(out)))
@@ -473,6 +506,8 @@ class Context:
 
     def verify_batch_prepared(self, proofs, prepared: np.ndarray, n: int) -> np.ndarray:
         x = np.ascontiguousarray(prepared, dtype=np.uint64)
+        self._check_vk_args(proofs, None, n)
+        self._check_words("prepared inputs", x, n * 8)
         out = np.zeros(n, dtype=np.uint8)
         pp = _ptr(proofs) if isinstance(proofs, np.ndarray) else C.cast(proofs, C.c_void_p)
         self.check(self.lib.g16_verify_batch_prepared(self.h, pp, _ptr(x), n, _ptr(out)))

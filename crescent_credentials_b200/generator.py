@@ -5,8 +5,13 @@ library's kernels -- Lagrange coefficients as one inverse NTT of the powers of t
 mat-vecs over the transposed matrices, and every query as fixed-base multiples of the canonical generators
 (generator.rs:34-35; gamma is whatever the caller passes, the fork uses 1 at generator.rs:28).
 
-It exists so that tests and the bench can mint *real* proving keys with a known trapdoor at full rs256 scale
-(proofs are then checkable in the exponent); it is not on the prove hot path."""
+Entry points, named as in the reference:
+    generate_random_parameters_with_reduction(ctx, matrices, rng, reduction)   generator.rs:19-47  (alpha, beta, delta <- rng,
+        gamma = 1 as in the fork, t <- sample_element_outside_domain(rng), canonical generators)
+    generate_parameters_with_qap(ctx, matrices, trapdoor, reduction)            generator.rs:50-228 with the toxic waste given
+
+Besides serving `zksetup`-style callers it lets tests and the bench mint *real* proving keys with a known trapdoor at full
+rs256 scale (proofs are then checkable in the exponent); it is not on the prove hot path."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -14,7 +19,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import ffi
-from .groth16 import ConstraintMatrices, ProvingKey, R_MOD, fr_to_mont
+from .groth16 import ConstraintMatrices, ProvingKey, R_MOD, fr_to_mont, sample_fr
 
 
 @dataclass
@@ -91,3 +96,27 @@ def generate_parameters_with_qap(ctx: ffi.Context, m: ConstraintMatrices, td: Tr
     pk.gamma_abc_g1 = g1(gamma_abc)
     qap = dict(a=a_w, b=b_w, c=c_w, l=l, hs=hs, zt=zt, n=n, gamma_abc=gamma_abc)
     return pk, qap
+
+
+def sample_element_outside_domain(rng, n: int) -> int:
+    """EvaluationDomain::sample_element_outside_domain (ark-poly 0.4): draw Fr::rand until Z(t) = t^n - 1 != 0."""
+    while True:
+        t = sample_fr(rng)
+        if pow(t, n, R_MOD) != 1:
+            return t
+
+
+def generate_random_parameters_with_reduction(ctx: ffi.Context, m: ConstraintMatrices, rng, reduction: str = "libsnark"):
+    """Groth16::generate_random_parameters_with_reduction (forks/groth16/src/generator.rs:19-47): alpha, beta, delta are drawn
+    from `rng` in that order, gamma is the constant 1 (fork, :28), the group generators are the canonical ones (:34-35), and t is
+    drawn afterwards by sample_element_outside_domain (:93).  `rng`: rng.StdRng (the rand 0.8 mirror) for a run that follows a
+    seeded reference run, or any CSPRNG exposing getrandbits(64).  Returns the ProvingKey; the toxic waste is dropped."""
+    alpha = sample_fr(rng)
+    beta = sample_fr(rng)
+    delta = sample_fr(rng)
+    n = domain_size(m.num_constraints, m.num_instance_variables)
+    if n > (1 << 28):
+        raise ffi.PolynomialDegreeTooLarge(ffi.ERR_DEGREE_TOO_LARGE, "no evaluation domain of that size (generator.rs:92)")
+    t = sample_element_outside_domain(rng, n)
+    pk, _ = generate_parameters_with_qap(ctx, m, Trapdoor(alpha, beta, 1, delta, t), reduction)
+    return pk

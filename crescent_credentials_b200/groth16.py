@@ -260,6 +260,83 @@ class ProvingKey:
         return pk
 
 
+    # -- CanonicalSerialize (uncompressed), the bytes creds/src/utils.rs:140-152 writes to prover_params.bin ------------------
+    def vk_parts(self):
+        """(gamma_g2 (16,), vk.delta_g1 (8,), gamma_abc_g1 (len, 8)) in this key's encoding, or None when the key carries no
+        verifying-key part (a hand-assembled prover-only key)."""
+        if hasattr(self, "raw_vk"):
+            rv = self.raw_vk
+            return (np.asarray(rv["gamma_g2"]).reshape(-1), np.asarray(rv["delta_g1"]).reshape(-1),
+                    np.asarray(rv["gamma_abc_g1"]).reshape(-1, 8))
+        if getattr(self, "gamma_g2", None) is not None and getattr(self, "gamma_abc_g1", None) is not None:
+            return (np.asarray(self.gamma_g2).reshape(-1), np.asarray(self.arrays["delta_g1"]).reshape(-1),
+                    np.asarray(self.gamma_abc_g1).reshape(-1, 8))
+        return None
+
+    def serialize_uncompressed(self, ctx: Optional["ffi.Context"] = None) -> bytes:
+        """ark-serialize 0.4 uncompressed bytes of ProvingKey{vk{alpha_g1, beta_g2, gamma_g2, delta_g1, delta_g2, gamma_abc_g1},
+        beta_g1, delta_g1, a_query, b_g1_query, b_g2_query, h_query, l_query} (data_structures.rs:31-44,101-118): coordinates
+        as 32-byte little-endian canonical integers, the y-sign / infinity flags in the two top bits of the last byte, every
+        Vec prefixed by its u64 length.  `ctx` (optional) converts Montgomery words on the GPU; without it the conversion is
+        byte marshalling with Python integers (fine for the test-size keys)."""
+        parts = self.vk_parts()
+        if parts is None:
+            raise ValueError("this ProvingKey has no verifying-key part (gamma_g2, gamma_abc_g1) to serialise")
+        gamma_g2, vk_delta_g1, gamma_abc = parts
+        canon = lambda a: _to_canonical_words(np.asarray(a, dtype=np.uint64), self.encoding, ctx)
+        g1 = lambda a: _ser_points_uncompressed(canon(a).reshape(-1, 8), 1)
+        g2 = lambda a: _ser_points_uncompressed(canon(a).reshape(-1, 16), 2)
+        vec = lambda a, f, w: struct.pack("<Q", np.asarray(a).reshape(-1, w).shape[0]) + f(a)
+        A = self.arrays
+        return b"".join([g1(A["alpha_g1"]), g2(A["beta_g2"]), g2(gamma_g2), g1(vk_delta_g1), g2(A["delta_g2"]),
+                         vec(gamma_abc, g1, 8), g1(A["beta_g1"]), g1(A["delta_g1"]), vec(A["a_query"], g1, 8),
+                         vec(A["b_g1_query"], g1, 8), vec(A["b_g2_query"], g2, 16), vec(A["h_query"], g1, 8),
+                         vec(A["l_query"], g1, 8)])
+
+
+_Q_HALF = (Q_MOD - 1) // 2
+
+
+def _to_canonical_words(a: np.ndarray, encoding: int, ctx=None) -> np.ndarray:
+    if encoding == ffi.ENC_CANONICAL or a.size == 0:
+        return np.ascontiguousarray(a, dtype=np.uint64)
+    flat = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    if ctx is not None:
+        return ctx.field_op(ffi.FIELD_FQ, ffi.OP_FROM_MONT, flat).reshape(a.shape)
+    return ints_to_limbs(fq_from_mont(flat)).reshape(a.shape)
+
+
+def _gt_half(y: np.ndarray) -> np.ndarray:
+    """y (n, 4) canonical little-endian words -> bool[n]: y > (q - 1) / 2, i.e. y is the larger of {y, -y}."""
+    half = [(_Q_HALF >> (64 * k)) & _MASK64 for k in range(4)]
+    gt = np.zeros(y.shape[0], dtype=bool)
+    eq = np.ones(y.shape[0], dtype=bool)
+    for k in (3, 2, 1, 0):
+        h = np.uint64(half[k])
+        gt |= eq & (y[:, k] > h)
+        eq &= y[:, k] == h
+    return gt
+
+
+def _ser_points_uncompressed(pts: np.ndarray, group: int) -> bytes:
+    """(n, 8) / (n, 16) canonical words, infinity = all zero -> n * 64 / n * 128 bytes with the SW flags (ark-ec 0.4
+    SWFlags: bit 7 = y is the lexicographically larger root, bit 6 = infinity) on the last byte."""
+    out = np.array(pts, dtype="<u8", order="C", copy=True)
+    n = out.shape[0]
+    if n == 0:
+        return b""
+    inf = ~out.any(axis=1)
+    if group == 1:
+        neg = _gt_half(out[:, 4:8])
+    else:  # Fq2 ordering: c1 first, then c0
+        c0, c1 = out[:, 8:12], out[:, 12:16]
+        neg = _gt_half(c1) | (~c1.any(axis=1) & _gt_half(c0))
+    last = out.shape[1] - 1
+    out[neg & ~inf, last] |= np.uint64(1 << 63)
+    out[inf, last] |= np.uint64(1 << 62)
+    return out.tobytes()
+
+
 class LibsnarkReduction:
     """R1CSToQAP implementation selector (forks/groth16/src/r1cs_to_qap.rs:100-226); the default of Groth16<E, QAP>
     (forks/groth16/src/lib.rs:55) and what Crescent uses (creds/src/lib.rs:229,283)."""
@@ -273,7 +350,9 @@ class CircomReduction:
 
 def sample_fr(rng) -> int:
     """Fr::rand shape (ark-ff 0.4): 4 x next_u64, top limb masked to 254 bits, rejection above the modulus; the accepted
-    integer is the Montgomery representation.  `rng` needs a .getrandbits(64)-style next_u64 (random.Random works)."""
+    integer is the Montgomery representation.  `rng` needs a .getrandbits(64)-style next_u64.  r and s are the
+    zero-knowledge blinders of the proof (prover.rs:151-152): production callers must pass a CSPRNG -- `secrets.SystemRandom()`
+    or the ChaCha `rng.StdRng` mirror seeded from OS entropy; `random.Random` is for reproducible tests only."""
     while True:
         v = 0
         for k in range(4):
@@ -292,8 +371,10 @@ class Groth16:
         self.ctx = ffi.Context(device, stream)
         self.qap = qap
         self.shard_rank, self.shard_count, self.precompute = shard_rank, shard_count, precompute
-        self._pk_id = None
-        self._mat_id = None
+        # the loaded objects themselves, not their id(): CPython reuses an id once an object is freed, and a different key at
+        # the same address must not be mistaken for the resident one
+        self._pk = None
+        self._matrices = None
 
     def close(self):
         self.ctx.close()
@@ -302,16 +383,18 @@ class Groth16:
     def _ensure_matrices(self, matrices: ConstraintMatrices, num_inputs: int, num_constraints: int):
         if num_inputs != matrices.num_instance_variables or num_constraints != matrices.num_constraints:
             raise ffi.G16Error(ffi.ERR_BAD_ARG, "num_inputs / num_constraints disagree with the matrices")
-        if self._mat_id != id(matrices):
+        if self._matrices is not matrices:
             m = matrices.num_instance_variables + matrices.num_witness_variables
+            self._matrices = None
             self.ctx.load_r1cs(matrices.num_constraints, matrices.num_instance_variables, m, matrices.row_ptr, matrices.col,
                                matrices.val, matrices.encoding)
-            self._mat_id = id(matrices)
+            self._matrices = matrices
 
     def _ensure_pk(self, pk: ProvingKey):
-        if self._pk_id != id(pk):
+        if self._pk is not pk:
+            self._pk = None
             self.ctx.load_pk(pk.arrays, pk.encoding, self.shard_rank, self.shard_count, self.precompute)
-            self._pk_id = id(pk)
+            self._pk = pk
 
     @staticmethod
     def _assignment(full_assignment) -> np.ndarray:

@@ -98,7 +98,10 @@ class Verifier:
     def __init__(self, device: int = 0, stream: int = 0, ctx: Optional[ffi.Context] = None):
         self.ctx = ctx if ctx is not None else ffi.Context(device, stream)
         self._own = ctx is None
-        self._pvk_id = None
+        # the prepared key this Verifier last loaded (the object, not its id()) and the context's load generation at that
+        # moment: another Verifier / caller sharing the context may have replaced the device key since
+        self._pvk = None
+        self._gen = -1
 
     def close(self):
         if self._own:
@@ -107,16 +110,18 @@ class Verifier:
     # -- verifier.rs:13-20 -------------------------------------------------------------------------------------------------
     def prepare_verifying_key(self, vk) -> PreparedVerifyingKey:
         arrays = vk if isinstance(vk, VkArrays) else (VkArrays.from_pk(vk) if isinstance(vk, ProvingKey) else VkArrays.from_vk(vk))
+        self._pvk = None
         self.ctx.load_vk(arrays.alpha_g1, arrays.beta_g2, arrays.gamma_g2, arrays.delta_g2, arrays.gamma_abc_g1, arrays.encoding)
         pvk = PreparedVerifyingKey(arrays, fq_from_mont(self.ctx.vk_alpha_beta().reshape(-1, 4)))
-        self._pvk_id = id(pvk)
+        self._pvk, self._gen = pvk, self.ctx.vk_generation
         return pvk
 
     def _ensure(self, pvk: PreparedVerifyingKey):
-        if self._pvk_id != id(pvk):
+        if self._pvk is not pvk or self._gen != self.ctx.vk_generation:
             a = pvk.vk
+            self._pvk = None
             self.ctx.load_vk(a.alpha_g1, a.beta_g2, a.gamma_g2, a.delta_g2, a.gamma_abc_g1, a.encoding)
-            self._pvk_id = id(pvk)
+            self._pvk, self._gen = pvk, self.ctx.vk_generation
 
     @staticmethod
     def _inputs(pvk: PreparedVerifyingKey, inputs_list) -> np.ndarray:
@@ -164,10 +169,12 @@ class Verifier:
         if not proofs:
             return []
         x = self._inputs(pvk, public_inputs)
-        return self._verdicts(self.ctx.verify_batch(proofs_to_ffi(proofs), x, len(proofs)))
+        return self._verdicts(self.ctx.verify_batch(proofs_to_ffi(proofs), x, len(proofs)), batched=len(proofs) > 1)
 
     @staticmethod
-    def _verdicts(v: np.ndarray) -> List[bool]:
-        if (v == ffi.VERDICT_UNEXPECTED_IDENTITY).any():
+    def _verdicts(v: np.ndarray, batched: bool = False) -> List[bool]:
+        """Single-proof calls raise UnexpectedIdentity like verifier.rs:62; in a batch one such proof must not discard the
+        other verdicts, so it reads as rejected (False) there."""
+        if not batched and (v == ffi.VERDICT_UNEXPECTED_IDENTITY).any():
             raise UnexpectedIdentity()
         return [bool(t == ffi.VERDICT_ACCEPT) for t in v]

@@ -60,12 +60,24 @@ def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
-def field_op(field, op, a, b=None):
+def field_op(field, op, a, b=None, threads=0):
+    """op codes of include/g16_b200.h (G16_OP_*): 0 mul, 1 add, 2 sub, 3 neg, 4 inv, 5 to_mont, 6 from_mont, 7 sqr,
+    8 mul by ONE broadcast element b, 9 add ONE broadcast element b."""
     a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
     out = np.empty_like(a)
     if b is not None:
         b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
-    lib().oc_field_op(field, op, _p(a), _p(b), _p(out), C.c_size_t(a.shape[0]))
+        assert b.shape[0] == (1 if op in (8, 9) else a.shape[0])
+    lib().oc_field_op_mt(field, op, _p(a), _p(b), _p(out), C.c_size_t(a.shape[0]), threads or hardware_threads())
+    return out
+
+
+def pow_table(base, scale, n, threads=0):
+    """out[i] = scale * base^i (Fr, Montgomery)."""
+    base = np.ascontiguousarray(base, dtype=np.uint64)
+    scale = np.ascontiguousarray(scale, dtype=np.uint64)
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().oc_pow_table(_p(base), _p(scale), C.c_size_t(n), _p(out), threads or hardware_threads())
     return out
 
 

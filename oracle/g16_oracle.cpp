@@ -646,40 +646,54 @@ extern "C" {
 
 int oc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
-void oc_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
-    for (size_t i = 0; i < n; i++) {
-        if (field == 0) {
-            Fr x, y, z;
-            memcpy(&x, a + 4 * i, 32);
-            if (b) memcpy(&y, b + 4 * i, 32);
-            switch (op) {
-                case 0: z = x * y; break;
-                case 1: z = x + y; break;
-                case 2: z = x - y; break;
-                case 3: z = x.neg(); break;
-                case 4: z = x.inverse(); break;
-                case 5: z = x.to_mont(); break;
-                case 6: z = x.from_mont(); break;
-                default: z = x.sqr();
-            }
-            memcpy(out + 4 * i, &z, 32);
-        } else {
-            Fq x, y, z;
-            memcpy(&x, a + 4 * i, 32);
-            if (b) memcpy(&y, b + 4 * i, 32);
-            switch (op) {
-                case 0: z = x * y; break;
-                case 1: z = x + y; break;
-                case 2: z = x - y; break;
-                case 3: z = x.neg(); break;
-                case 4: z = x.inverse(); break;
-                case 5: z = x.to_mont(); break;
-                case 6: z = x.from_mont(); break;
-                default: z = x.sqr();
-            }
-            memcpy(out + 4 * i, &z, 32);
+}  // extern "C"
+template <class F>
+static void field_op_range(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t lo, size_t hi) {
+    const bool bcast = op == 8 || op == 9;  // b is ONE element (same op codes as include/g16_b200.h: G16_OP_*)
+    F yb = F::zero();
+    if (bcast && b) memcpy(&yb, b, 32);
+    for (size_t i = lo; i < hi; i++) {
+        F x, y = yb, z;
+        memcpy(&x, a + 4 * i, 32);
+        if (b && !bcast) memcpy(&y, b + 4 * i, 32);
+        switch (op) {
+            case 0: case 8: z = x * y; break;
+            case 1: case 9: z = x + y; break;
+            case 2: z = x - y; break;
+            case 3: z = x.neg(); break;
+            case 4: z = x.inverse(); break;
+            case 5: z = x.to_mont(); break;
+            case 6: z = x.from_mont(); break;
+            default: z = x.sqr();
         }
+        memcpy(out + 4 * i, &z, 32);
     }
+}
+
+extern "C" {
+void oc_field_op_mt(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, int threads) {
+    parallel_for(n, threads, [&](size_t lo, size_t hi) {
+        if (field == 0) field_op_range<Fr>(op, a, b, out, lo, hi);
+        else field_op_range<Fq>(op, a, b, out, lo, hi);
+    });
+}
+void oc_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    oc_field_op_mt(field, op, a, b, out, n, n >= 4096 ? (int)std::thread::hardware_concurrency() : 1);
+}
+
+// out[i] = scale * base^i (Montgomery in / out)
+void oc_pow_table(const uint64_t* base, const uint64_t* scale, size_t n, uint64_t* out, int threads) {
+    Fr b, s;
+    memcpy(&b, base, 32);
+    memcpy(&s, scale, 32);
+    Fr* o = (Fr*)out;
+    parallel_for(n, threads, [&](size_t lo, size_t hi) {
+        Fr cur = s * b.pow_u64(lo);
+        for (size_t i = lo; i < hi; i++) {
+            o[i] = cur;
+            cur = cur * b;
+        }
+    });
 }
 
 // arkworks-semantics transform, natural order in/out, in place
@@ -730,56 +744,58 @@ void oc_msm_g2(const uint64_t* points, const uint64_t* scalars, size_t n, uint64
     memcpy(out, &a, sizeof(a));
 }
 
-// out[i] = k_i * G (canonical generators), via an 8-bit fixed-base window table
-void oc_fixed_base(int group, const uint64_t* scalars, size_t n, uint64_t* out, int threads) {
+}  // extern "C"
+// out[i] = k_i * G (canonical generators), via an 8-bit fixed-base window table; Jacobian results are normalised
+// 256 at a time with one shared inversion (ark-ec's batch normalisation, Projective::normalize_batch)
+template <class F>
+static void fixed_base_t(const Aff<F>& gen, const Fr* scalars, size_t n, Aff<F>* out, int threads) {
     const unsigned W = 8, NW = 32;
-    if (group == 1) {
-        std::vector<G1A> tbl((size_t)NW << W);
-        G1J base = G1J::from_affine(g1_gen());
-        for (unsigned w = 0; w < NW; w++) {
-            G1J cur = G1J::inf();
-            tbl[(size_t)w << W] = G1A{Fq::zero(), Fq::zero()};
-            for (unsigned d = 1; d < (1u << W); d++) {
-                cur.add(base);
-                tbl[((size_t)w << W) + d] = cur.to_affine();
-            }
-            for (unsigned k = 0; k < W; k++) base = base.dbl();
+    std::vector<Aff<F>> tbl((size_t)NW << W);
+    Jac<F> base = Jac<F>::from_affine(gen);
+    for (unsigned w = 0; w < NW; w++) {
+        Jac<F> cur = Jac<F>::inf();
+        tbl[(size_t)w << W] = Aff<F>{F::zero(), F::zero()};
+        for (unsigned d = 1; d < (1u << W); d++) {
+            cur.add(base);
+            tbl[((size_t)w << W) + d] = cur.to_affine();
         }
-        parallel_for(n, threads, [&](size_t lo, size_t hi) {
-            for (size_t i = lo; i < hi; i++) {
-                Fr c = ((const Fr*)scalars)[i].from_mont();
-                G1J acc = G1J::inf();
-                for (unsigned w = 0; w < NW; w++) {
-                    unsigned d = (c.l[w / 8] >> ((w % 8) * 8)) & 0xff;
-                    if (d) acc.add_mixed(tbl[((size_t)w << W) + d]);
-                }
-                ((G1A*)out)[i] = acc.to_affine();
-            }
-        });
-    } else {
-        std::vector<G2A> tbl((size_t)NW << W);
-        G2J base = G2J::from_affine(g2_gen());
-        for (unsigned w = 0; w < NW; w++) {
-            G2J cur = G2J::inf();
-            tbl[(size_t)w << W] = G2A{Fq2::zero(), Fq2::zero()};
-            for (unsigned d = 1; d < (1u << W); d++) {
-                cur.add(base);
-                tbl[((size_t)w << W) + d] = cur.to_affine();
-            }
-            for (unsigned k = 0; k < W; k++) base = base.dbl();
-        }
-        parallel_for(n, threads, [&](size_t lo, size_t hi) {
-            for (size_t i = lo; i < hi; i++) {
-                Fr c = ((const Fr*)scalars)[i].from_mont();
-                G2J acc = G2J::inf();
-                for (unsigned w = 0; w < NW; w++) {
-                    unsigned d = (c.l[w / 8] >> ((w % 8) * 8)) & 0xff;
-                    if (d) acc.add_mixed(tbl[((size_t)w << W) + d]);
-                }
-                ((G2A*)out)[i] = acc.to_affine();
-            }
-        });
+        for (unsigned k = 0; k < W; k++) base = base.dbl();
     }
+    const size_t B = 256;
+    parallel_tasks((n + B - 1) / B, threads, [&](size_t blk) {
+        size_t lo = blk * B, hi = std::min(n, lo + B);
+        Jac<F> acc[B];
+        F pre[B];
+        F run = F::one();
+        for (size_t i = lo; i < hi; i++) {
+            Fr c = scalars[i].from_mont();
+            Jac<F> a = Jac<F>::inf();
+            for (unsigned w = 0; w < NW; w++) {
+                unsigned d = (c.l[w / 8] >> ((w % 8) * 8)) & 0xff;
+                if (d) a.add_mixed(tbl[((size_t)w << W) + d]);
+            }
+            acc[i - lo] = a;
+            pre[i - lo] = run;
+            if (!a.is_inf()) run = run * a.z;
+        }
+        F inv = run.inverse();
+        for (size_t i = hi; i-- > lo;) {
+            const Jac<F>& a = acc[i - lo];
+            if (a.is_inf()) {
+                out[i] = Aff<F>{F::zero(), F::zero()};
+                continue;
+            }
+            F zi = inv * pre[i - lo];
+            inv = inv * a.z;
+            F zi2 = zi.sqr();
+            out[i] = Aff<F>{a.x * zi2, a.y * zi2 * zi};
+        }
+    });
+}
+extern "C" {
+void oc_fixed_base(int group, const uint64_t* scalars, size_t n, uint64_t* out, int threads) {
+    if (group == 1) fixed_base_t<Fq>(g1_gen(), (const Fr*)scalars, n, (G1A*)out, threads);
+    else fixed_base_t<Fq2>(g2_gen(), (const Fr*)scalars, n, (G2A*)out, threads);
 }
 
 // instance_map_with_evaluation (r1cs_to_qap.rs:106-148): a, b, c receive m Montgomery elements each; returns Z(t) in zt

@@ -407,3 +407,49 @@ def test_spmv_sliced_ell_ragged_rows(gpu_ctx):
             assert np.array_equal(h0, h1), red
     finally:
         ctx.close()
+
+
+# ---- row f-2: the key generator against the committed key bytes ------------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_generator_reproduces_golden_key_bytes(gpu_ctx, name):
+    """generate_parameters_with_qap on the GPU (forks/groth16/src/generator.rs:50-228; gamma = 1 and vk.delta_g1 as in the fork;
+    both h_query conventions: r1cs_to_qap.rs:215-225 and qap.rs:92-107) serialises to the committed arkworks-layout key, byte for
+    byte -- the same bytes the oracle's generator produced."""
+    import ast
+    from crescent_credentials_b200 import generator
+    meta, r1cs_bytes, pk_bytes = load_golden(name)
+    mats = load_matrices(r1cs_bytes)
+    td = ast.literal_eval(meta["trapdoor"]) if isinstance(meta["trapdoor"], str) else meta["trapdoor"]
+    td = generator.Trapdoor(*(int(td[k], 16) for k in ("alpha", "beta", "gamma", "delta", "t")))
+    pk, _ = generator.generate_parameters_with_qap(gpu_ctx, mats, td, reduction=meta["reduction"])
+    assert pk.serialize_uncompressed(gpu_ctx) == pk_bytes
+    assert pk.serialize_uncompressed() == pk_bytes   # same bytes through the integer marshalling path
+
+
+def test_generate_random_parameters_follows_the_reference_draw_order(gpu_ctx):
+    """generate_random_parameters_with_reduction (generator.rs:19-47,93): alpha, beta, delta, then t from the same StdRng stream;
+    gamma = 1.  The key equals generate_parameters_with_qap under the toxic waste drawn by hand, and a proof under it verifies."""
+    from crescent_credentials_b200 import generator, rng, verifier
+    meta, r1cs_bytes, _ = load_golden("rand100")
+    mats = load_matrices(r1cs_bytes)
+    pk = generator.generate_random_parameters_with_reduction(gpu_ctx, mats, rng.StdRng.seed_from_u64(42))
+    r2 = rng.StdRng.seed_from_u64(42)
+    alpha, beta, delta = g.sample_fr(r2), g.sample_fr(r2), g.sample_fr(r2)
+    t = generator.sample_element_outside_domain(r2, 128)
+    want, _ = generator.generate_parameters_with_qap(gpu_ctx, mats, generator.Trapdoor(alpha, beta, 1, delta, t))
+    assert pk.serialize_uncompressed(gpu_ctx) == want.serialize_uncompressed(gpu_ctx)
+    assert g1_gamma_is_generator(pk)
+    prover, ver = g.Groth16(0), verifier.Verifier(0)
+    try:
+        z = [int(v, 16) for v in meta["z"]]
+        proof = prover.create_random_proof_with_reduction(pk, mats, mats.num_instance_variables, mats.num_constraints, z, r2)
+        assert ver.verify(pk, z[1:mats.num_instance_variables], proof) is True
+        assert ver.verify(pk, [z[1] + 1] + z[2:mats.num_instance_variables], proof) is False
+    finally:
+        prover.close()
+        ver.close()
+
+
+def g1_gamma_is_generator(pk) -> bool:
+    """gamma = 1 (generator.rs:28): vk.gamma_g2 is the canonical G2 generator."""
+    return g.g2_from_mont(np.asarray(pk.gamma_g2)) == o.G2_GEN
