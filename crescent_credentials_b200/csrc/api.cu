@@ -117,6 +117,7 @@ static void free_r1cs(g16_ctx* ctx) {
     ctx->d_z = ctx->d_a = ctx->d_b = ctx->d_c = nullptr;
     ctx->have_r1cs = false;
     ctx->witness_resident = false;
+    ctx->witness_partial = false;
 }
 
 void g16_ctx_destroy(g16_ctx* ctx) {
@@ -339,6 +340,23 @@ int g16_msm_run_dev(g16_ctx* ctx, int slot, const void* scalars_dev, size_t n, u
     return G16_OK;
 }
 
+int g16_msm_copy_result_dev(g16_ctx* ctx, int slot, void* dst_dev) {
+    if (!ctx || !dst_dev || slot < 0 || slot >= kMsmSlots) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "msm_copy_result: bad argument") : G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    const MsmBases* mb = &ctx->slot[slot];
+    if (mb->group == 0) return set_err(ctx, G16_ERR_BAD_ARG, "msm slot %d has no bases", slot);
+    const size_t bytes = mb->group == 1 ? sizeof(G1XYZZ) : sizeof(G2XYZZ);
+    if (ctx->slot_scratch[slot].result) G16_CUDA(ctx, cudaMemcpyAsync(dst_dev, ctx->slot_scratch[slot].result, bytes, cudaMemcpyDeviceToDevice, ctx->main));
+    else G16_CUDA(ctx, cudaMemsetAsync(dst_dev, 0, bytes, ctx->main));  // an empty share: the point at infinity (zz = 0)
+    return G16_OK;
+}
+int g16_msm_combine_dev(g16_ctx* ctx, int group, const void* partials_dev, int count, uint64_t* out, int* out_inf) {
+    if (!ctx || !partials_dev || !out || count < 1 || (group != 1 && group != 2))
+        return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "msm_combine: bad argument") : G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    return sum_partials_to_affine_host(ctx, group, partials_dev, count, out, out_inf, ctx->main);
+}
+
 static int fixed_base_host(g16_ctx* ctx, int group, const uint64_t* scalars, size_t n, uint64_t* out) {
     if (!ctx || (n && (!scalars || !out))) return G16_ERR_BAD_ARG;
     if (n == 0) return G16_OK;
@@ -439,6 +457,7 @@ static int upload_witness(g16_ctx* ctx, const uint64_t* z, cudaStream_t st) {
     if (!z) return set_err(ctx, G16_ERR_BAD_ARG, "witness pointer is NULL");
     G16_CUDA(ctx, cudaMemcpyAsync(ctx->d_z, z, ctx->m * 32, cudaMemcpyHostToDevice, st));
     ctx->witness_resident = true;
+    ctx->witness_partial = true;
     return G16_OK;
 }
 
@@ -447,6 +466,26 @@ int g16_upload_witness(g16_ctx* ctx, const uint64_t* z) {
     Guard g(ctx);
     G16_TRY(upload_witness(ctx, z, ctx->main));
     G16_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    return G16_OK;
+}
+
+int g16_upload_witness_async(g16_ctx* ctx, const uint64_t* z, int shard_only) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "no R1CS loaded");
+    if (!z) return set_err(ctx, G16_ERR_BAD_ARG, "witness pointer is NULL");
+    if (!shard_only) return upload_witness(ctx, z, ctx->main);
+    if (!ctx->have_pk) return set_err(ctx, G16_ERR_BAD_ARG, "upload_witness_async(shard_only): no proving key loaded");
+    // the wire MSMs of this rank read z[1 + lo, 1 + hi) (a / b_g1 / b_g2, prover.rs:84-89) and, when l_query is not laid out on
+    // a's index space, z[ni + l_lo, ni + l_hi) (l, prover.rs:70-74): nothing else of the 32 * m bytes has to cross PCIe
+    ctx->witness_resident = false;
+    const size_t lo = ctx->sh_lo[Q_A], hi = ctx->sh_hi[Q_A];
+    if (hi > lo)
+        G16_CUDA(ctx, cudaMemcpyAsync(ctx->d_z + 1 + lo, z + 4 * (1 + lo), (hi - lo) * 32, cudaMemcpyHostToDevice, ctx->main));
+    if (!ctx->l_on_a_space && ctx->sh_hi[Q_L] > ctx->sh_lo[Q_L])
+        G16_CUDA(ctx, cudaMemcpyAsync(ctx->d_z + ctx->ni + ctx->sh_lo[Q_L], z + 4 * (ctx->ni + ctx->sh_lo[Q_L]),
+                                      (ctx->sh_hi[Q_L] - ctx->sh_lo[Q_L]) * 32, cudaMemcpyHostToDevice, ctx->main));
+    ctx->witness_partial = true;
     return G16_OK;
 }
 
@@ -571,6 +610,7 @@ static int load_pk_ranges(g16_ctx* ctx, const g16_pk_view* pk, int shard_rank, i
     // l's shard always follows a's (the ranks' l ranges must partition l_query whatever each rank decides about sharing)
     size_t l_lo, l_hi;
     const bool aligned = pk->l_len <= m1;
+    ctx->l_on_a_space = aligned;
     const size_t shift = aligned ? m1 - pk->l_len : 0;  // = num_instance - 1
     if (aligned) {
         l_lo = (lo > shift ? lo : shift) - shift;
@@ -849,6 +889,7 @@ static int prove_full(g16_ctx* ctx, const uint64_t* z, const uint64_t* r, const 
     // (r, s, pk)-only scalar multiplications overlap everything else
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
     G16_CUDA(ctx, cudaStreamWaitEvent(ctx->side[4], ctx->ev_fork, 0));
+    ctx->pre_pending = false;  // the AsmPre slot is about to hold THIS call's (r, s): a g16_prove_prepare before it is void
     G16_TRY(assemble_pre(ctx, r, s, ctx->side[4]));
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_join[4], ctx->side[4]));
     G16_TRY(prove_shard_streams(ctx, r, s, reduction));
@@ -899,7 +940,9 @@ int g16_prove_shard_begin_dev(g16_ctx* ctx, const uint64_t r[4], const uint64_t 
     if (!r || !s) return set_err(ctx, G16_ERR_BAD_ARG, "prove_shard_begin: null r/s");
     Guard g(ctx);
     G16_TRY(check_ready(ctx));
-    if (!ctx->witness_resident) return set_err(ctx, G16_ERR_BAD_ARG, "prove_shard_begin_dev: no witness uploaded");
+    if (!(ctx->witness_resident || (ctx->witness_partial && !run_witness_map)))
+        return set_err(ctx, G16_ERR_BAD_ARG, run_witness_map ? "prove_shard_begin_dev: the witness map needs the whole witness on the device"
+                                                              : "prove_shard_begin_dev: no witness uploaded");
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[14], ctx->main));
     G16_TRY(shard_begin(ctx, r, s, reduction, run_witness_map != 0));
     ctx->shard_open = true;
@@ -969,6 +1012,7 @@ int g16_prove_combine_dev(g16_ctx* ctx, const void* dev_partials, int count, con
         // g16_prove_prepare already ran the (r, s)-only scalar multiplications on a side stream: just join it
         G16_CUDA(ctx, cudaStreamWaitEvent(ctx->main, ctx->ev_join[4], 0));
     } else {
+        ctx->pre_pending = false;
         G16_TRY(assemble_pre(ctx, r, s, ctx->main));
     }
     ctx->pre_pending = false;

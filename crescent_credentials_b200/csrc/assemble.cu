@@ -200,8 +200,11 @@ __global__ void k_assemble_post(const AsmPre* pre, const PartialDev* parts, int 
 }
 
 template <class F>
-__global__ void k_xyzz_to_affine(const XYZZ<F>* in, Affine<F>* out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *out = in->to_affine();
+__global__ void k_xyzz_to_affine(const XYZZ<F>* in, Affine<F>* out, int count) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> acc = in[0];
+    for (int i = 1; i < count; i++) acc.add(in[i]);
+    *out = acc.to_affine();
 }
 
 static AsmConsts consts_of(const g16_ctx* ctx) {
@@ -278,15 +281,19 @@ int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, g16_proof*
 }
 
 int xyzz_to_affine_host(g16_ctx* ctx, int group, const void* xyzz_dev, uint64_t* out, int* out_inf, cudaStream_t st) {
+    return sum_partials_to_affine_host(ctx, group, xyzz_dev, 1, out, out_inf, st);
+}
+
+int sum_partials_to_affine_host(g16_ctx* ctx, int group, const void* xyzz_dev, int count, uint64_t* out, int* out_inf, cudaStream_t st) {
     if (group == 1) {
-        G16_LAUNCH(ctx, k_xyzz_to_affine<Fq>, 1, 32, 0, st, (const G1XYZZ*)xyzz_dev, (G1Affine*)affine_ptr(ctx));
+        G16_LAUNCH(ctx, k_xyzz_to_affine<Fq>, 1, 32, 0, st, (const G1XYZZ*)xyzz_dev, (G1Affine*)affine_ptr(ctx), count);
         G1Affine h;
         G16_CUDA(ctx, cudaMemcpyAsync(&h, affine_ptr(ctx), sizeof(h), cudaMemcpyDeviceToHost, st));
         G16_CUDA(ctx, cudaStreamSynchronize(st));
         memcpy(out, &h, sizeof(h));
         if (out_inf) *out_inf = h.is_inf();
     } else {
-        G16_LAUNCH(ctx, k_xyzz_to_affine<Fq2>, 1, 32, 0, st, (const G2XYZZ*)xyzz_dev, (G2Affine*)affine_ptr(ctx));
+        G16_LAUNCH(ctx, k_xyzz_to_affine<Fq2>, 1, 32, 0, st, (const G2XYZZ*)xyzz_dev, (G2Affine*)affine_ptr(ctx), count);
         G2Affine h;
         G16_CUDA(ctx, cudaMemcpyAsync(&h, affine_ptr(ctx), sizeof(h), cudaMemcpyDeviceToHost, st));
         G16_CUDA(ctx, cudaStreamSynchronize(st));

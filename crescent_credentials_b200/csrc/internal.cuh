@@ -138,7 +138,9 @@ struct g16_ctx {
     g16::Fr *d_z = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;  // witness + three n-vectors
     uint64_t* h_pinned = nullptr;                                           // pinned staging for z
     size_t h_pinned_bytes = 0;
-    bool witness_resident = false;
+    bool witness_resident = false;  // all m elements of z are on the device
+    bool witness_partial = false;   // at least this rank's wire-MSM slice of z is (g16_upload_witness_async(shard_only))
+    bool l_on_a_space = false;      // l_query laid out on a_query[1..]'s index space (always, for a Groth16 key): l reads a's z slice
 
     // proving key
     bool have_pk = false;
@@ -274,6 +276,8 @@ G2Affine g2_generator();
 int scale_point_dev(g16_ctx* ctx, const void* in_xyzz, const uint64_t* k_mont, void* out_xyzz, cudaStream_t st);
 int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, g16_proof* out, cudaStream_t st);
 int xyzz_to_affine_host(g16_ctx* ctx, int group, const void* xyzz_dev, uint64_t* out, int* out_inf, cudaStream_t st);
+// sum of `count` XYZZ points -> one affine point on the host (the combine step of a point-range sharded MSM)
+int sum_partials_to_affine_host(g16_ctx* ctx, int group, const void* xyzz_dev, int count, uint64_t* out, int* out_inf, cudaStream_t st);
 
 // verify.cu ---------------------------------------------------------------------------------------------------------------
 void verify_free(g16_ctx* ctx);

@@ -30,6 +30,7 @@ EXPORTS = [
     "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count", "g16_set_option",
     "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare", "g16_get_msm_stats", "g16_ctx_load_pk_ranges",
     "g16_prove_shard_begin_dev", "g16_prove_shard_finish_dev", "g16_copy_h_dev",
+    "g16_upload_witness_async", "g16_msm_copy_result_dev", "g16_msm_combine_dev",
     "g16_ctx_load_vk", "g16_vk_alpha_beta", "g16_prepare_inputs", "g16_verify_batch", "g16_verify_batch_prepared",
     "g16_verify_batch_dev", "g16_pairing", "g16_host_alloc", "g16_host_free",
 ]
@@ -124,6 +125,7 @@ def load_library() -> C.CDLL:
     lib.g16_ctx_load_r1cs.argtypes = [C.c_void_p, C.POINTER(R1csView)]
     lib.g16_prove.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ProofOut)]
     lib.g16_upload_witness.argtypes = [C.c_void_p, C.c_void_p]
+    lib.g16_upload_witness_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.g16_prove_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ProofOut)]
     lib.g16_prove_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Partial)]
     lib.g16_prove_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
@@ -141,6 +143,8 @@ def load_library() -> C.CDLL:
     lib.g16_msm_set_bases.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
     lib.g16_msm_set_bases_dev.argtypes = lib.g16_msm_set_bases.argtypes
     lib.g16_msm_run_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]
+    lib.g16_msm_copy_result_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.g16_msm_combine_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
     lib.g16_ntt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int]
     lib.g16_ntt_dev.argtypes = lib.g16_ntt.argtypes
     lib.g16_field_op.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -241,6 +245,38 @@ class Context:
         fn = self.lib.g16_msm_g1 if group == 1 else self.lib.g16_msm_g2
         self.check(fn(self.h, _ptr(points), _ptr(scalars), n, _ptr(out), C.byref(inf)))
         return out, bool(inf.value)
+
+    # resident MSM slots (bases stay on the device; the synthetic sweep and the sharded stand-alone MSM)
+    def msm_set_bases_dev(self, slot: int, group: int, points_dev: int, n: int, window_bits: int = 0, precompute: bool = False):
+        self.check(self.lib.g16_msm_set_bases_dev(self.h, slot, group, C.c_void_p(points_dev), n, window_bits, int(precompute)))
+        self._slot_group = getattr(self, "_slot_group", {})
+        self._slot_group[slot] = group
+
+    def msm_run_dev(self, slot: int, scalars_dev: int, n: int, want_result: bool = True):
+        """Runs the MSM of `slot` over n device scalars; want_result: returns (affine words, is_infinity), else queues only."""
+        if not want_result:
+            self.check(self.lib.g16_msm_run_dev(self.h, slot, C.c_void_p(scalars_dev), n, None, None))
+            return None
+        out = np.zeros(16, dtype=np.uint64)
+        inf = C.c_int(0)
+        self.check(self.lib.g16_msm_run_dev(self.h, slot, C.c_void_p(scalars_dev), n, _ptr(out), C.byref(inf)))
+        return out[:8 * getattr(self, "_slot_group", {}).get(slot, 2)].copy(), bool(inf.value)
+
+    def msm_copy_result_dev(self, slot: int, dst_dev: int):
+        self.check(self.lib.g16_msm_copy_result_dev(self.h, slot, C.c_void_p(dst_dev)))
+
+    def msm_combine_dev(self, group: int, partials_dev: int, count: int):
+        out = np.zeros(8 if group == 1 else 16, dtype=np.uint64)
+        inf = C.c_int(0)
+        self.check(self.lib.g16_msm_combine_dev(self.h, group, C.c_void_p(partials_dev), count, _ptr(out), C.byref(inf)))
+        return out, bool(inf.value)
+
+    def fixed_base_dev(self, group: int, scalars_dev: int, n: int, out_dev: int):
+        fn = self.lib.g16_fixed_base_g1_dev if group == 1 else self.lib.g16_fixed_base_g2_dev
+        self.check(fn(self.h, C.c_void_p(scalars_dev), n, C.c_void_p(out_dev)))
+
+    def ntt_dev(self, data_dev: int, log_n: int, inverse: bool = False, coset: bool = False):
+        self.check(self.lib.g16_ntt_dev(self.h, C.c_void_p(data_dev), log_n, int(inverse), int(coset)))
 
     def fixed_base(self, group: int, scalars: np.ndarray) -> np.ndarray:
         scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
@@ -384,6 +420,14 @@ class Context:
             z = np.ascontiguousarray(z, dtype=np.uint64)
             self._check_z(z)
         self.check(self.lib.g16_upload_witness(self.h, _ptr(z)))
+
+    def upload_witness_async(self, z, shard_only: bool = False):
+        """Stream-ordered upload (no synchronisation): z must stay valid until the context's stream has passed the copy, so
+        pass page-locked memory (an address, or an array that outlives the proof).  shard_only: just this rank's slice."""
+        if isinstance(z, np.ndarray):
+            z = np.ascontiguousarray(z, dtype=np.uint64)
+            self._check_z(z)
+        self.check(self.lib.g16_upload_witness_async(self.h, _ptr(z), int(shard_only)))
 
     def prove_resident(self, r, s, reduction=REDUCTION_LIBSNARK) -> ProofOut:
         r = np.ascontiguousarray(r, dtype=np.uint64)

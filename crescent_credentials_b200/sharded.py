@@ -10,7 +10,8 @@ Two plans:
              spend that time on a LARGER share of the z-only MSMs (a, l, b_g1, b_g2); rank 0 then scatters the h
              coefficients (n*32/G bytes per peer, one NCCL scatter over NVLink) and every rank finishes with its h-MSM
              range.  Rank 0's share f0 of the wire MSMs balances  wm + f0*Z  against  (1 - f0)*Z/(G - 1).
-The witness goes host -> each GPU directly in both plans."""
+The witness goes host -> each GPU directly in both plans; a rank that does not run the witness map uploads only the slice of z
+its wire MSMs read (g16_upload_witness_async(shard_only)), stream-ordered, without a host synchronisation."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -87,15 +88,31 @@ def scatter_h(h_all, h_mine, plan: ShardPlan, rank: int):
 
 
 class ShardedProver:
-    """Groth16 prover whose MSMs are sharded over torch.distributed ranks (call collectively on every rank)."""
+    """Groth16 prover whose MSMs are sharded over torch.distributed ranks (call collectively on every rank).
 
-    def __init__(self, pk: ProvingKey, matrices: ConstraintMatrices, device: int, rank: int, world: int, stream: int = 0,
-                 precompute: bool = False, plan: Optional[ShardPlan] = None):
+    Stream discipline: the library's asynchronous entry points (`*_dev`) run on the context's main stream and the
+    torch.distributed collectives on torch's *current* stream; the two are only ordered if they are the same stream.  The
+    prover therefore owns (or is given) ONE torch.cuda.Stream, hands its raw handle to the context as the main stream, and
+    issues every collective inside `torch.cuda.stream(self.stream)`: scatter -> h MSM -> partial copy -> all_gather ->
+    combine is a single stream-ordered chain, with no host synchronisation before the proof read-back on rank 0."""
+
+    def __init__(self, pk: ProvingKey, matrices: ConstraintMatrices, device: int, rank: int, world: int, stream=None,
+                 precompute: bool = False, plan: Optional[ShardPlan] = None, ctx: Optional[ffi.Context] = None):
+        """stream: a torch.cuda.Stream (default: a new one on `device`).  ctx: an existing context that was created on that
+        stream's handle (its R1CS / key are loaded here); default: a new context."""
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
-        self.ctx = ffi.Context(device, stream)
+        dev = torch.device("cuda", device)
+        if ctx is not None and stream is None:
+            raise ValueError("ShardedProver(ctx=...) needs the torch stream the context was created on")
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=dev)
+        if not isinstance(self.stream, torch.cuda.Stream):
+            raise TypeError("stream must be a torch.cuda.Stream: collectives and library calls have to share it")
+        self._own_ctx = ctx is None
+        self.ctx = ctx if ctx is not None else ffi.Context(device, self.stream.cuda_stream)
         m = matrices.num_instance_variables + matrices.num_witness_variables
+        self.m = m
         self.ctx.load_r1cs(matrices.num_constraints, matrices.num_instance_variables, m, matrices.row_ptr, matrices.col,
                            matrices.val, matrices.encoding)
         h_len = int(np.asarray(pk.arrays["h_query"]).reshape(-1, 8).shape[0])
@@ -104,45 +121,78 @@ class ShardedProver:
         assert self.plan.world == world
         self.ctx.load_pk(pk.arrays, pk.encoding, rank, world, precompute, h_range=self.plan.h_ranges[rank],
                          z_range=self.plan.z_ranges[rank])
-        dev = f"cuda:{device}"
-        self.mine = torch.zeros((ffi.PARTIAL_U64,), dtype=torch.int64, device=dev)
-        self.h_all = self.h_mine = None
-        if self.plan.staggered:
-            n = self.ctx.domain_size()
-            cap = max(n, world * self.plan.h_chunk)
-            if rank == self.plan.wm_rank:
-                self.h_all = torch.zeros((cap, 4), dtype=torch.int64, device=dev)
-            self.h_mine = torch.zeros((self.plan.h_chunk, 4), dtype=torch.int64, device=dev)
+        with torch.cuda.stream(self.stream):
+            self.mine = torch.zeros((ffi.PARTIAL_U64,), dtype=torch.int64, device=dev)
+            self.gathered = torch.zeros((world, ffi.PARTIAL_U64), dtype=torch.int64, device=dev)
+            self.h_all = self.h_mine = None
+            if self.plan.staggered:
+                n = self.ctx.domain_size()
+                cap = max(n, world * self.plan.h_chunk)
+                if rank == self.plan.wm_rank:
+                    self.h_all = torch.zeros((cap, 4), dtype=torch.int64, device=dev)
+                self.h_mine = torch.zeros((self.plan.h_chunk, 4), dtype=torch.int64, device=dev)
+        self.stream.synchronize()
+        self.z_pin = None          # page-locked staging of the witness for prove()
+        self._z_done = None        # event: the last upload from z_pin has been consumed
+
+    @property
+    def runs_witness_map(self) -> bool:
+        return (not self.plan.staggered) or self.rank == self.plan.wm_rank
+
+    def upload_witness(self, z_host):
+        """Stream-ordered upload of this rank's part of the witness: the whole of z on a rank that runs the witness map,
+        only the slice its wire MSMs read elsewhere.  z_host: a page-locked host ADDRESS (int) of m x 4 u64 words that stays
+        valid until the proof is done, or a numpy array (then staged through an internal page-locked buffer)."""
+        torch = self.torch
+        if isinstance(z_host, np.ndarray):
+            z = np.ascontiguousarray(z_host, dtype=np.uint64).reshape(-1, 4)
+            if z.shape[0] != self.m:
+                raise ffi.G16Error(ffi.ERR_BAD_ARG, f"witness has {z.shape[0]} elements, the R1CS {self.m} wires")
+            if self.z_pin is None:
+                self.z_pin = torch.empty((self.m, 4), dtype=torch.int64).pin_memory()
+                self._z_done = torch.cuda.Event()
+            else:
+                self._z_done.synchronize()   # the previous proof's copy must have left the staging buffer
+            self.z_pin.numpy()[:] = z.view(np.int64)
+            self.ctx.upload_witness_async(self.z_pin.data_ptr(), shard_only=not self.runs_witness_map)
+            with torch.cuda.stream(self.stream):
+                self._z_done.record()
+        else:
+            self.ctx.upload_witness_async(int(z_host), shard_only=not self.runs_witness_map)
 
     def prove_resident(self, rr, ss, reduction=ffi.REDUCTION_LIBSNARK):
-        """Witness already uploaded; (rr, ss) Montgomery.  Returns the raw proof on rank 0, None elsewhere."""
+        """Witness already uploaded (upload_witness); (rr, ss) Montgomery.  Returns the raw proof on rank 0, None elsewhere."""
+        import torch.distributed as dist
         ctx, plan, rank = self.ctx, self.plan, self.rank
-        if rank == 0:
-            ctx.prove_prepare(rr, ss)   # overlaps r*delta, s*delta, ... with the shard MSMs
-        if plan.staggered:
-            owner = rank == plan.wm_rank
-            ctx.prove_shard_begin_dev(rr, ss, reduction, run_witness_map=owner)
-            if owner:
-                ctx.copy_h_dev(self.h_all.data_ptr(), self.h_all.shape[0])
-            scatter_h(self.h_all, self.h_mine, plan, rank)
-            if owner:
-                ctx.prove_shard_finish_dev()
+        with self.torch.cuda.stream(self.stream):
+            if rank == 0:
+                ctx.prove_prepare(rr, ss)   # overlaps r*delta, s*delta, ... with the shard MSMs
+            if plan.staggered:
+                owner = rank == plan.wm_rank
+                ctx.prove_shard_begin_dev(rr, ss, reduction, run_witness_map=owner)
+                if owner:
+                    ctx.copy_h_dev(self.h_all.data_ptr(), self.h_all.shape[0])
+                scatter_h(self.h_all, self.h_mine, plan, rank)   # the one exchange step: n*32/G bytes to every peer
+                if owner:
+                    ctx.prove_shard_finish_dev()
+                else:
+                    ctx.prove_shard_finish_dev(self.h_mine.data_ptr(), plan.h_ranges[rank][0], plan.h_chunk)
             else:
-                ctx.prove_shard_finish_dev(self.h_mine.data_ptr(), plan.h_ranges[rank][0], plan.h_chunk)
-        else:
-            ctx.prove_shard_dev(rr, ss, reduction)
-        ctx.copy_partial_dev(self.mine.data_ptr())
-        allp = gather_partials(self.mine, self.world)
-        if rank != 0:
-            return None
-        return ctx.prove_combine_dev(allp.data_ptr(), self.world, rr, ss)
+                ctx.prove_shard_dev(rr, ss, reduction)
+            ctx.copy_partial_dev(self.mine.data_ptr())
+            dist.all_gather_into_tensor(self.gathered.view(-1), self.mine)
+            if rank != 0:
+                return None
+            return ctx.prove_combine_dev(self.gathered.data_ptr(), self.world, rr, ss)
 
     def prove(self, z_mont, r: int, s: int, reduction=ffi.REDUCTION_LIBSNARK) -> Optional[Proof]:
         """z_mont: (m, 4) uint64 Montgomery witness (same on every rank).  Returns the proof on rank 0, None elsewhere."""
         rr, ss = fr_to_mont([r % R_MOD])[0], fr_to_mont([s % R_MOD])[0]
-        self.ctx.upload_witness(z_mont)
+        self.upload_witness(z_mont)
         raw = self.prove_resident(rr, ss, reduction)
         return None if raw is None else Proof.from_ffi(raw)
 
     def close(self):
-        self.ctx.close()
+        self.stream.synchronize()
+        if self._own_ctx:
+            self.ctx.close()

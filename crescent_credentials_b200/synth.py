@@ -40,16 +40,17 @@ def splitmix64(x: np.ndarray) -> np.ndarray:
         return z ^ (z >> np.uint64(31))
 
 
-def stream(seed: int, tag: int, n: int, lane: int = 0) -> np.ndarray:
+def stream(seed: int, tag: int, n: int, lane: int = 0, first: int = 0) -> np.ndarray:
+    """Elements [first, first + n) of the stream (seed, tag, lane): a rank can draw its own slice of a long vector."""
     base = np.uint64((seed ^ (tag << 40) ^ (lane << 56)) & 0xFFFFFFFFFFFFFFFF)
-    return splitmix64(np.arange(n, dtype=np.uint64) ^ base)
+    return splitmix64(np.arange(first, first + n, dtype=np.uint64) ^ base)
 
 
-def uniform_fr_canonical(seed: int, tag: int, n: int) -> np.ndarray:
-    """n elements uniform in [0, 2^253) as canonical little-endian limbs (2^253 < r)."""
+def uniform_fr_canonical(seed: int, tag: int, n: int, first: int = 0) -> np.ndarray:
+    """n elements uniform in [0, 2^253) as canonical little-endian limbs (2^253 < r); elements [first, first + n) of the stream."""
     out = np.empty((n, 4), dtype=np.uint64)
     for k in range(4):
-        out[:, k] = stream(seed, tag, n, lane=k + 1)
+        out[:, k] = stream(seed, tag, n, lane=k + 1, first=first)
     out[:, 3] &= np.uint64((1 << 61) - 1)
     return out
 

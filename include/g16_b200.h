@@ -157,6 +157,12 @@ int g16_prove(g16_ctx* ctx, const uint64_t* z, const uint64_t r[4], const uint64
 /* Same, witness already resident on the device (g16_upload_witness): no H2D inside. */
 int g16_upload_witness(g16_ctx* ctx, const uint64_t* z);
 int g16_prove_resident(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], int reduction, g16_proof* out);
+/* Stream-ordered witness upload for the sharded path: queues the copy on the context's main stream and returns without
+ * synchronising (z must stay valid, ideally page-locked, until the stream has passed it; the prove calls that follow on the same
+ * context are ordered behind it).  shard_only != 0 copies only the slice of z this rank's wire MSMs read (z[1 + lo, 1 + hi) of its
+ * a / b_g1 / b_g2 / l ranges): enough for every rank that does not run the witness map itself (g16_prove_shard_begin_dev with
+ * run_witness_map = 0), which must not pay for the other 32 * m * (1 - 1/G) bytes. */
+int g16_upload_witness_async(g16_ctx* ctx, const uint64_t* z, int shard_only);
 
 /* MSM-sharded proving: every rank calls g16_prove_shard on its context (loaded with its shard) with the same (r, s), the
  * G partials are gathered (one small NCCL gather by the host glue) and rank 0 calls g16_prove_combine. */
@@ -213,6 +219,12 @@ int g16_msm_set_bases(g16_ctx* ctx, int slot, int group /*1|2*/, const uint64_t*
 int g16_msm_set_bases_dev(g16_ctx* ctx, int slot, int group, const void* points_dev, size_t n, int window_bits,
                           int precompute);
 int g16_msm_run_dev(g16_ctx* ctx, int slot, const void* scalars_dev, size_t n, uint64_t* out, int* out_inf);
+/* Point-range sharding of a stand-alone MSM (the pattern of g16_prove_shard / g16_prove_combine for one sum): every
+ * rank runs g16_msm_run_dev over its contiguous share of the pairs with out = NULL, copies its partial sum (XYZZ: 16 u64 words
+ * for G1, 32 for G2) to dst_dev with g16_msm_copy_result_dev -- stream-ordered, so that one all_gather on the same stream can
+ * follow -- and one rank adds the `count` gathered partials and normalises with g16_msm_combine_dev. */
+int g16_msm_copy_result_dev(g16_ctx* ctx, int slot, void* dst_dev);
+int g16_msm_combine_dev(g16_ctx* ctx, int group, const void* partials_dev, int count, uint64_t* out, int* out_inf);
 
 /* In-place NTT over Fr of size 2^log_n, natural order in and out (arkworks semantics): inverse includes 1/n; coset
  * applies the shift g = Fr::GENERATOR = 5 (fft: scale then transform; ifft: transform then unscale). */

@@ -61,7 +61,8 @@ def test_staggered_plan_matches_golden(name, world, share):
             ctxs.append(ctx)
             ctx.load_r1cs(mats.num_constraints, mats.num_instance_variables, wires, mats.row_ptr, mats.col, mats.val, mats.encoding)
             ctx.load_pk(pk.arrays, pk.encoding, rank, world, h_range=plan.h_ranges[rank], z_range=plan.z_ranges[rank])
-            ctx.upload_witness(z)
+            # a rank that does not run the witness map uploads only the slice of z its wire MSMs read (stream-ordered, no sync)
+            ctx.upload_witness_async(z, shard_only=(rank != 0))
         r, s = g.fr_to_mont([int(meta["r"], 16)])[0], g.fr_to_mont([int(meta["s"], 16)])[0]
         n = ctxs[0].domain_size()
         cap = max(n, world * plan.h_chunk)
@@ -82,6 +83,9 @@ def test_staggered_plan_matches_golden(name, world, share):
         assert proof.serialize_uncompressed().hex() == meta["proof_uncompressed"]
         with pytest.raises(ffi.G16Error):   # finish without begin
             ctxs[0].prove_shard_finish_dev()
+        if world > 1:
+            with pytest.raises(ffi.G16Error):   # the witness map needs the whole witness, this rank only holds its slice
+                ctxs[1].prove_shard_begin_dev(r, s, reduction, run_witness_map=True)
         ctxs[0].prove_shard_begin_dev(r, s, reduction, run_witness_map=False)
         with pytest.raises(ffi.G16Error):   # h chunk that does not cover the rank's range
             ctxs[0].prove_shard_finish_dev(h_all, plan.h_ranges[0][1] + 1, 1)
@@ -89,3 +93,46 @@ def test_staggered_plan_matches_golden(name, world, share):
     finally:
         for ctx in ctxs:
             ctx.close()
+
+
+def test_prepare_then_other_prove_does_not_reuse_stale_scalars():
+    """g16_prove_prepare(r, s) followed by a full prove with OTHER scalars on the same context, then combine(r, s): the
+    assembly must not pick up the (r2, s2) points the full prove left in the shared slot (advisor finding, api.cu)."""
+    meta, r1cs_bytes, pk_bytes = load_golden("rand300")
+    mats = load_matrices(r1cs_bytes)
+    pk = g.ProvingKey.deserialize_uncompressed_unchecked(pk_bytes)
+    wires = mats.num_instance_variables + mats.num_witness_variables
+    z = g.fr_to_mont([int(v, 16) for v in meta["z"]])
+    r, s = g.fr_to_mont([int(meta["r"], 16)])[0], g.fr_to_mont([int(meta["s"], 16)])[0]
+    r2, s2 = g.fr_to_mont([12345])[0], g.fr_to_mont([67890])[0]
+    shard, full = ffi.Context(0), ffi.Context(0)
+    try:
+        for ctx in (shard, full):
+            ctx.load_r1cs(mats.num_constraints, mats.num_instance_variables, wires, mats.row_ptr, mats.col, mats.val, mats.encoding)
+            ctx.load_pk(pk.arrays, pk.encoding, 0, 1)
+        part = shard.prove_shard(z, r, s)
+        full.prove_prepare(r, s)
+        other = g.Proof.from_ffi(full.prove(z, r2, s2))
+        assert other.serialize_uncompressed().hex() != meta["proof_uncompressed"]
+        proof = g.Proof.from_ffi(full.prove_combine(part.reshape(1, -1), r, s))
+        assert proof.serialize_uncompressed().hex() == meta["proof_uncompressed"]
+    finally:
+        shard.close()
+        full.close()
+
+
+def test_sharded_prover_class_over_nccl():
+    """The ShardedProver class itself, one process per GPU over NCCL (2 ranks): staggered and uniform plans, numpy and
+    page-locked witnesses, proofs back to back; rank 0 compares the bytes with the golden fixture.  Needs two GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(here, "sharded_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "SHARDED_WORKER_OK" in out.stdout

@@ -13,7 +13,7 @@ echo "pytest(alt) rc=$?"; tail -2 gpurun_out/ab_mul3_pytest.log
 for lib in "" "$ALT"; do
   tag=$([ -z "$lib" ] && echo default || echo mul3)
   G16_LIB=${lib:-$PWD/crescent_credentials_b200/libg16b200.so} timeout 200 python tools/verify_bench.py --sizes 1 65536 --reps 3 > gpurun_out/ab_mul3_verify_$tag.jsonl 2>&1
-  G16_LIB=${lib:-$PWD/crescent_credentials_b200/libg16b200.so} timeout 200 python bench.py --no-cpu-baseline --inflight 0 > gpurun_out/ab_mul3_bench_$tag.json 2>/dev/null
+  G16_LIB=${lib:-$PWD/crescent_credentials_b200/libg16b200.so} timeout 200 python bench.py --no-cpu-baseline --inflight 0 --extras '' > gpurun_out/ab_mul3_bench_$tag.json 2>/dev/null
   python - "$tag" <<'PY'
 import json, sys
 tag = sys.argv[1]

@@ -10,7 +10,7 @@ timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "s
 timeout 300 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.log; echo "bench rc=$? $(( $(date +%s) - t0 ))s"; cut -c1-400 gpurun_out/bench_n1.json
 timeout 300 python bench.py --what verify > gpurun_out/verify_bench.jsonl 2> gpurun_out/verify_bench.err; echo "verify rc=$? $(( $(date +%s) - t0 ))s"; cut -c1-700 gpurun_out/verify_bench.jsonl; tail -3 gpurun_out/verify_bench.err
 for w in S-2^12 S-2^16; do
-  timeout 200 python bench.py --workload $w --no-cpu-baseline --inflight 0 --steps 50 > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.log; echo "$w rc=$?"
+  timeout 200 python bench.py --workload $w --no-cpu-baseline --inflight 0 --steps 50 --extras "" > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.log; echo "$w rc=$?"
   python -c "
 import json,sys
 d=json.loads(open('gpurun_out/bench_$w.json').read().strip().splitlines()[-1]); print('$w', d['ms_per_step'], d['e2e']['ms_per_step'], d['stage_ms'])"

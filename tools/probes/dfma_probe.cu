@@ -5,7 +5,7 @@
 // result is compared with the integer product's.
 #include <cstdio>
 #include <cstdlib>
-#include "../../crescent_credentials_b200/csrc/fp_dfma.cuh"
+#include "fp_dfma.cuh"
 using namespace g16;
 
 __global__ void k_dfma(double* out, int iters) {

@@ -13,7 +13,7 @@
 //
 // The same source runs on the host (tests/host_fp_shim.cpp) with std::fma under FE_TOWARDZERO.
 #pragma once
-#include "fp.cuh"
+#include "../../crescent_credentials_b200/csrc/fp.cuh"
 #if !defined(__CUDA_ARCH__)
 #include <cmath>
 #include <cstring>
