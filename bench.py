@@ -362,6 +362,7 @@ def main():
     with ClockSampler(local_rank) as clk:
         ms_res = timed(torch, dist, world, run.step_resident, args.steps)
     launches = ctx.launch_count() - launches0
+    graph_stats = ctx.graph_stats()   # launches replayed as CUDA graphs count as the kernels they stand for
     stage = ctx.timings() if world == 1 else {}
     # ---- timed region 2: end to end through the public call, host witness -------------------------------------------
     ms_e2e = timed(torch, dist, world, run.step_e2e, args.steps)
@@ -474,7 +475,7 @@ def main():
             "data": "synthetic", "config": cfg_main,
             "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(inst.z_mont.nbytes), "d2h_bytes_per_step": 256},
-            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,
+            "gpu_launches": int(launches), "graph": graph_stats, "clocks": clk.summary(), "roofline": roof,
             "accumulation_stage": acc_stage, "pipelined": pipelined, "cpu_baseline": cpu, "stage_ms": stage,
             "rank_stage_ms": rank_stage, "proof_verified_in_exponent": verified, "proof_sha256": sha,
             "prove_ms": ms_res / args.steps, "extra": extras,

@@ -35,10 +35,20 @@ struct ProofDev {
 struct Scalar256 {
     uint32_t w[8];
 };
+// (r, s, r*s) in canonical form + the r == 0 flag (prover.rs:102), written per proof into ctx->d_small by assemble_set_scalars.
+// The kernels read them from device memory rather than taking them by value: the launch sequence of a proof is then the same
+// from proof to proof, which is what lets api.cu replay it as a CUDA graph.
+struct AsmScalars {
+    Scalar256 r, s, rs;
+    int r_is_zero;
+    int pad[7];
+};
 
-__global__ void k_assemble_pre(AsmConsts k, Scalar256 r, Scalar256 s, Scalar256 rs, int r_is_zero, AsmPre* out) {
+__global__ void k_assemble_pre(AsmConsts k, const AsmScalars* __restrict__ sc, AsmPre* out) {
     unsigned wid = threadIdx.x >> 5;
     if (threadIdx.x & 31) return;  // no barrier in this kernel
+    const Scalar256 r = sc->r, s = sc->s, rs = sc->rs;
+    const int r_is_zero = sc->r_is_zero;
     if (wid == 0) {
         G1XYZZ t = scalar_mul(G1XYZZ::from_affine(k.delta_g1), r.w);
         t.madd(k.a0);
@@ -124,11 +134,13 @@ __device__ __forceinline__ void warp_tree_sum(XYZZ<F>* sh, unsigned lane) {  // 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(160) k_assemble_pre_tables(const AsmTables* __restrict__ T, Scalar256 r, Scalar256 s, Scalar256 rs,
-                                                             int r_is_zero, AsmPre* out) {
+__global__ void __launch_bounds__(160) k_assemble_pre_tables(const AsmTables* __restrict__ T, const AsmScalars* __restrict__ sc,
+                                                             AsmPre* out) {
     __shared__ G1XYZZ sh1[4][32];  // r*delta_g1, rs*delta_g1, s*U, r*V
     __shared__ G2XYZZ sh2[32];     // s*delta_g2
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const Scalar256 r = sc->r, s = sc->s, rs = sc->rs;
+    const int r_is_zero = sc->r_is_zero;
     auto byte_of = [&](const Scalar256& k) { return (k.w[lane >> 2] >> (8 * (lane & 3))) & 0xffu; };
     if (wid < 4) {
         const Scalar256& k = wid == 0 ? r : wid == 1 ? rs : wid == 2 ? s : r;
@@ -164,8 +176,11 @@ __global__ void __launch_bounds__(160) k_assemble_pre_tables(const AsmTables* __
 }
 
 // out = k * in for one G1 point (one lane; latency-bound, runs beside the remaining MSMs)
-__global__ void k_scale_point(const G1XYZZ* __restrict__ in, Scalar256 k, G1XYZZ* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *out = scalar_mul(*in, k.w);
+__global__ void k_scale_point(const G1XYZZ* __restrict__ in, const Scalar256* __restrict__ k, G1XYZZ* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const Scalar256 kk = *k;
+        *out = scalar_mul(*in, kk.w);
+    }
 }
 
 // partial layout (u64 words): h[16] l[16] a[16] s*a[16] r*b_g1[16] b_g2[32]  == 5 x G1XYZZ + 1 x G2XYZZ
@@ -234,10 +249,30 @@ static Scalar256 canon(const Fr& m) {
     return s;
 }
 
-// d_small layout: [AsmPre][ProofDev][generic affine scratch]
+// d_small layout: [AsmPre @0][ProofDev @1024][generic affine scratch @2048][AsmScalars @2560][msm_can_share counters @3072]
 static AsmPre* pre_ptr(g16_ctx* ctx) { return (AsmPre*)ctx->d_small; }
 static ProofDev* proof_ptr(g16_ctx* ctx) { return (ProofDev*)((char*)ctx->d_small + 1024); }
 static void* affine_ptr(g16_ctx* ctx) { return (char*)ctx->d_small + 2048; }
+static AsmScalars* scalars_ptr(g16_ctx* ctx) { return (AsmScalars*)((char*)ctx->d_small + 2560); }
+static_assert(sizeof(AsmPre) <= 1024 && sizeof(ProofDev) <= 1024 && sizeof(G2Affine) <= 512 && sizeof(AsmScalars) <= 512, "d_small layout");
+
+// (r, s) of the proof being queued -> device (stream-ordered; staged through the context's page-locked block so that the copy
+// is a true asynchronous DMA and the staging memory outlives the call)
+int assemble_set_scalars(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, cudaStream_t st) {
+    Fr rm = fr_load(r), sm = fr_load(s);
+    Fr rs = rm * sm;
+    if (!ctx->h_scalars) G16_CUDA(ctx, cudaHostAlloc(&ctx->h_scalars, 2 * sizeof(AsmScalars), cudaHostAllocDefault));
+    // two slots, alternating: the previous proof's copy may still be in flight when the next one is queued (the *_dev entry
+    // points do not synchronise)
+    AsmScalars* h = (AsmScalars*)ctx->h_scalars + (ctx->h_scalars_slot ^= 1);
+    memset(h, 0, sizeof(*h));
+    h->r = canon(rm);
+    h->s = canon(sm);
+    h->rs = canon(rs);
+    h->r_is_zero = (int)rm.is_zero();
+    G16_CUDA(ctx, cudaMemcpyAsync(scalars_ptr(ctx), h, sizeof(AsmScalars), cudaMemcpyHostToDevice, st));
+    return G16_OK;
+}
 
 // per-key tables for k_assemble_pre_tables; called by g16_ctx_load_pk once the single points are in the context
 int assemble_build_tables(g16_ctx* ctx, cudaStream_t st) {
@@ -246,30 +281,36 @@ int assemble_build_tables(g16_ctx* ctx, cudaStream_t st) {
     return G16_OK;
 }
 
-int assemble_pre(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, cudaStream_t st) {
-    Fr rm = fr_load(r), sm = fr_load(s);
-    Fr rs = rm * sm;
+// the scalars must already be on the device (assemble_set_scalars, ordered before `st`)
+int assemble_pre(g16_ctx* ctx, cudaStream_t st) {
     if (ctx->opt_asm_tables && ctx->d_asm_tables) {
-        G16_LAUNCH(ctx, k_assemble_pre_tables, 1, 160, 0, st, (const AsmTables*)ctx->d_asm_tables, canon(rm), canon(sm), canon(rs),
-                   (int)rm.is_zero(), pre_ptr(ctx));
+        G16_LAUNCH(ctx, k_assemble_pre_tables, 1, 160, 0, st, (const AsmTables*)ctx->d_asm_tables, (const AsmScalars*)scalars_ptr(ctx),
+                   pre_ptr(ctx));
         return G16_OK;
     }
-    G16_LAUNCH(ctx, k_assemble_pre, 1, 128, 0, st, consts_of(ctx), canon(rm), canon(sm), canon(rs), (int)rm.is_zero(), pre_ptr(ctx));
+    G16_LAUNCH(ctx, k_assemble_pre, 1, 128, 0, st, consts_of(ctx), (const AsmScalars*)scalars_ptr(ctx), pre_ptr(ctx));
     return G16_OK;
 }
 
-int scale_point_dev(g16_ctx* ctx, const void* in_xyzz, const uint64_t* k_mont, void* out_xyzz, cudaStream_t st) {
-    G16_LAUNCH(ctx, k_scale_point, 1, 32, 0, st, (const G1XYZZ*)in_xyzz, canon(fr_load(k_mont)), (G1XYZZ*)out_xyzz);
+// which = 0: k = r, 1: k = s (of the scalars assemble_set_scalars put on the device)
+int scale_point_dev(g16_ctx* ctx, const void* in_xyzz, int which, void* out_xyzz, cudaStream_t st) {
+    const Scalar256* k = which == 0 ? &scalars_ptr(ctx)->r : &scalars_ptr(ctx)->s;
+    G16_LAUNCH(ctx, k_scale_point, 1, 32, 0, st, (const G1XYZZ*)in_xyzz, k, (G1XYZZ*)out_xyzz);
     return G16_OK;
 }
 
-int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, g16_proof* out, cudaStream_t st) {
+int assemble_proof_queue(g16_ctx* ctx, const void* partials_dev, int count, cudaStream_t st) {
     G16_LAUNCH(ctx, k_assemble_post, 1, 128, 0, st, (const AsmPre*)pre_ptr(ctx), (const PartialDev*)partials_dev, count,
                proof_ptr(ctx));
-    G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[15], st));
+    if (ctx->capturing) G16_CUDA(ctx, cudaEventRecordWithFlags(ctx->ev_t[15], st, cudaEventRecordExternal));
+    else G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[15], st));
+    G16_CUDA(ctx, cudaMemcpyAsync(ctx->h_proof, proof_ptr(ctx), sizeof(ProofDev), cudaMemcpyDeviceToHost, st));
+    return G16_OK;
+}
+
+void assemble_proof_read(g16_ctx* ctx, g16_proof* out) {
     ProofDev host;
-    G16_CUDA(ctx, cudaMemcpyAsync(&host, proof_ptr(ctx), sizeof(ProofDev), cudaMemcpyDeviceToHost, st));
-    G16_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(&host, ctx->h_proof, sizeof(host));
     memset(out, 0, sizeof(*out));
     memcpy(out->a, &host.a, 64);
     memcpy(out->b, &host.b, 128);
@@ -277,7 +318,6 @@ int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, g16_proof*
     out->a_inf = host.a.is_inf();
     out->b_inf = host.b.is_inf();
     out->c_inf = host.c.is_inf();
-    return G16_OK;
 }
 
 int xyzz_to_affine_host(g16_ctx* ctx, int group, const void* xyzz_dev, uint64_t* out, int* out_inf, cudaStream_t st) {

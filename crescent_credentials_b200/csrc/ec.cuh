@@ -133,7 +133,7 @@ struct XYZZ {
     G16_HD_NOINLINE Affine<F> to_affine() const {
         if (is_inf()) return Affine<F>::inf();
         // one inversion: i3 = 1/zzz, and zz^3 = zzz^2  =>  1/zz = zz^2 / zzz^2 = (zz * i3)^2
-        F i3 = zzz.inverse_bgcd();
+        F i3 = zzz.inverse_fast();
         F t = zz * i3;
         F i2 = t.sqr();
         return Affine<F>{x * i2, y * i3};

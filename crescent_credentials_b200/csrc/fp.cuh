@@ -461,6 +461,63 @@ struct alignas(16) Fp {
         r1 = out[1];
         r2 = out[2];
     }
+    // Two independent Montgomery products in lock-step (same scheme as mul_cios3): four carry chains in flight per thread.
+    // k_ba_add uses it for the two products that hang off the running inverse (inv_den = run * prefix, run = run * den), which
+    // are independent of each other.  Bit-identical to two mul_cios calls.
+    static G16_HD void mul_cios2(const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, Fp& r0, Fp& r1) {
+        uint32_t A[2][8], B[2][8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            A[0][k] = a0.v[k], A[1][k] = a1.v[k];
+            B[0][k] = b0.v[k], B[1][k] = b1.v[k];
+        }
+        uint32_t X[2][8], Y[2][8];
+        uint32_t m[2], cy[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            lanes_mul(X[j], A[j][0], A[j][2], A[j][4], A[j][6], B[j][0]);
+            lanes_mul(Y[j], A[j][1], A[j][3], A[j][5], A[j][7], B[j][0]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            m[j] = X[j][0] * PR::INV;
+            lanes_mad(Y[j], PR::P(1), PR::P(3), PR::P(5), PR::P(7), m[j]);
+            cy[j] = lanes_mad(X[j], PR::P(0), PR::P(2), PR::P(4), PR::P(6), m[j]);
+            Y[j][7] += cy[j];
+        }
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                uint32_t* ev = (i & 1) ? Y[j] : X[j];
+                uint32_t* od = (i & 1) ? X[j] : Y[j];
+                lanes_fold_shift_mad(ev[0], od, A[j][1], A[j][3], A[j][5], A[j][7], B[j][i]);
+                cy[j] = lanes_mad(ev, A[j][0], A[j][2], A[j][4], A[j][6], B[j][i]);
+                od[7] += cy[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                uint32_t* ev = (i & 1) ? Y[j] : X[j];
+                uint32_t* od = (i & 1) ? X[j] : Y[j];
+                m[j] = ev[0] * PR::INV;
+                lanes_mad(od, PR::P(1), PR::P(3), PR::P(5), PR::P(7), m[j]);
+                cy[j] = lanes_mad(ev, PR::P(0), PR::P(2), PR::P(4), PR::P(6), m[j]);
+                od[7] += cy[j];
+            }
+        }
+        Fp out[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            uint32_t sh[8];
+#pragma unroll
+            for (int k = 0; k < 7; k++) sh[k] = Y[j][k + 1];
+            sh[7] = 0;
+            uint32_t c = add8(out[j].v, sh, X[j]);
+            reduce_once(out[j].v, c);
+        }
+        r0 = out[0];
+        r1 = out[1];
+    }
     // Montgomery reduction of a 16-limb value P < p * 2^256:  P * 2^-256 mod p, fully reduced.
     // Same two-accumulator scheme as mul_cios with the product rows removed: the high limbs of P enter one per round
     // at the top of the accumulator.
@@ -610,6 +667,184 @@ struct alignas(16) Fp {
         for (int i = 0; i < 8; i++) r3.v[i] = PR::R3(i);
         return y * r3;  // * R^3 / R  =>  value^-1 * R
     }
+
+    // ---- inverse by divsteps (Bernstein-Yang "safegcd", the variable-time form of libsecp256k1's modinv32) -----------------
+    // The binary GCD above touches all eight limbs of four 256-bit values in every one of its ~400-500 iterations: ~100 us for
+    // the lone lane that inverts in k_ba_invert -- five of those per MSM chain are the largest fixed latency of a small MSM
+    // (25 x 0.12 ms per proof).  divsteps decide everything from the LOW bits of (f, g): 30 steps run on one
+    // 32-bit word each and yield a 2x2 transition matrix, which is then applied once to the full-size values -- about 20 rounds of
+    // ~40 word-multiplications instead of ~450 rounds of multi-limb shifts and subtractions.  Same value as inverse() /
+    // inverse_bgcd() (the inverse is unique); inverse of 0 is 0.  Values travel as nine signed 30-bit limbs.
+    struct S30 {
+        int32_t v[9];
+    };
+    static G16_HD unsigned ctz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+        return (unsigned)(__ffs((int)x) - 1);
+#else
+        return (unsigned)__builtin_ctz(x);
+#endif
+    }
+    static G16_HD uint32_t p_inv30() {  // p^-1 mod 2^30 (Newton from p = p^-1 mod 8)
+        uint32_t p0 = PR::P(0), x = p0;
+        x *= 2u - p0 * x;
+        x *= 2u - p0 * x;
+        x *= 2u - p0 * x;
+        x *= 2u - p0 * x;
+        return x & 0x3FFFFFFFu;
+    }
+    static G16_HD void to_s30(S30& o, const uint32_t* w) {  // 8 x 32 unsigned -> 9 x 30
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const int bit = 30 * i, k = bit >> 5, sh = bit & 31;
+            uint64_t two = w[k];
+            if (k + 1 < 8) two |= (uint64_t)w[k + 1] << 32;
+            o.v[i] = (int32_t)((uint32_t)(two >> sh) & 0x3FFFFFFFu);
+        }
+    }
+    // 30 divsteps on the low words; returns the new eta and the transition matrix t = (u v; q r), entries in (-2^30, 2^30]
+    static G16_HD int32_t divsteps_30(int32_t eta, uint32_t f0, uint32_t g0, int32_t* t) {
+        uint32_t u = 1, v = 0, q = 0, r = 1, f = f0, g = g0;
+        int i = 30;
+        for (;;) {
+            const unsigned zeros = ctz32(g | (0xFFFFFFFFu << i));  // sentinel: never more than i
+            g >>= zeros;
+            u <<= zeros;
+            v <<= zeros;
+            eta -= (int32_t)zeros;
+            i -= (int)zeros;
+            if (i == 0) break;
+            if (eta < 0) {
+                uint32_t tmp;
+                eta = -eta;
+                tmp = f, f = g, g = 0u - tmp;
+                tmp = u, u = q, q = 0u - tmp;
+                tmp = v, v = r, r = 0u - tmp;
+            }
+            // cancel up to min(i, eta + 1, 6) low bits of g with a multiple of f:  w = -g / f mod 2^limit,  -1/f = f (f^2 - 2) mod 64
+            int limit = (eta + 1) > i ? i : (eta + 1);
+            const uint32_t m = (0xFFFFFFFFu >> (32 - limit)) & 63u;
+            const uint32_t w = (f * g * (f * f - 2u)) & m;
+            g += f * w;
+            q += u * w;
+            r += v * w;
+        }
+        t[0] = (int32_t)u, t[1] = (int32_t)v, t[2] = (int32_t)q, t[3] = (int32_t)r;
+        return eta;
+    }
+    // (f, g) <- t (f, g) / 2^30, exactly
+    static G16_HD void update_fg_30(S30& f, S30& g, const int32_t* t) {
+        const int64_t u = t[0], v = t[1], q = t[2], r = t[3];
+        int64_t cf = u * f.v[0] + v * g.v[0];
+        int64_t cg = q * f.v[0] + r * g.v[0];
+        cf >>= 30;
+        cg >>= 30;
+#pragma unroll
+        for (int i = 1; i < 9; i++) {
+            const int64_t fi = f.v[i], gi = g.v[i];
+            cf += u * fi + v * gi;
+            cg += q * fi + r * gi;
+            f.v[i - 1] = (int32_t)cf & 0x3FFFFFFF;
+            cf >>= 30;
+            g.v[i - 1] = (int32_t)cg & 0x3FFFFFFF;
+            cg >>= 30;
+        }
+        f.v[8] = (int32_t)cf;
+        g.v[8] = (int32_t)cg;
+    }
+    // (d, e) <- t (d, e) / 2^30 mod p, staying in (-2p, p)
+    static G16_HD void update_de_30(S30& d, S30& e, const int32_t* t, const S30& P, uint32_t pinv30) {
+        const int32_t u = t[0], v = t[1], q = t[2], r = t[3];
+        const int32_t sd = d.v[8] >> 31, se = e.v[8] >> 31;  // all-ones when negative
+        int32_t md = (u & sd) + (v & se);
+        int32_t me = (q & sd) + (r & se);
+        int64_t cd = (int64_t)u * d.v[0] + (int64_t)v * e.v[0];
+        int64_t ce = (int64_t)q * d.v[0] + (int64_t)r * e.v[0];
+        // multiples of p that zero the low 30 bits
+        md -= (int32_t)((pinv30 * (uint32_t)cd + (uint32_t)md) & 0x3FFFFFFFu);
+        me -= (int32_t)((pinv30 * (uint32_t)ce + (uint32_t)me) & 0x3FFFFFFFu);
+        cd += (int64_t)P.v[0] * md;
+        ce += (int64_t)P.v[0] * me;
+        cd >>= 30;
+        ce >>= 30;
+#pragma unroll
+        for (int i = 1; i < 9; i++) {
+            cd += (int64_t)u * d.v[i] + (int64_t)v * e.v[i] + (int64_t)P.v[i] * md;
+            ce += (int64_t)q * d.v[i] + (int64_t)r * e.v[i] + (int64_t)P.v[i] * me;
+            d.v[i - 1] = (int32_t)cd & 0x3FFFFFFF;
+            cd >>= 30;
+            e.v[i - 1] = (int32_t)ce & 0x3FFFFFFF;
+            ce >>= 30;
+        }
+        d.v[8] = (int32_t)cd;
+        e.v[8] = (int32_t)ce;
+    }
+    G16_HD_NOINLINE Fp inverse_safegcd() const {
+        if (is_zero()) return zero();
+        S30 P, f, g, d, e;
+        uint32_t pw[8];
+        load_p(pw);
+        to_s30(P, pw);
+        f = P;
+        to_s30(g, v);
+#pragma unroll
+        for (int i = 0; i < 9; i++) d.v[i] = 0, e.v[i] = 0;
+        e.v[0] = 1;
+        const uint32_t pinv30 = p_inv30();
+        int32_t eta = -1;
+        for (int it = 0; it < 40; it++) {  // <= 25 rounds suffice for 256-bit inputs; the bound only guards against misuse
+            int32_t t[4];
+            eta = divsteps_30(eta, (uint32_t)f.v[0], (uint32_t)g.v[0], t);
+            update_de_30(d, e, t, P, pinv30);
+            update_fg_30(f, g, t);
+            int32_t nz = 0;
+#pragma unroll
+            for (int i = 0; i < 9; i++) nz |= g.v[i];
+            if (nz == 0) break;
+        }
+        // now f = +-1 and d = +-(this->v as an integer)^-1 mod p, d in (-2p, p): fix the sign, then bring d into [0, p)
+        const int32_t fneg = f.v[8] >> 31;
+        int32_t c = 0;
+        const int32_t dneg = d.v[8] >> 31;
+#pragma unroll
+        for (int i = 0; i < 9; i++) d.v[i] += P.v[i] & dneg;         // d < 0: add p  -> (-p, p)
+#pragma unroll
+        for (int i = 0; i < 9; i++) d.v[i] = (d.v[i] ^ fneg) - fneg;  // f = -1: negate
+#pragma unroll
+        for (int i = 0; i < 8; i++) {                                  // propagate carries, limbs back to [0, 2^30)
+            d.v[i] += c;
+            c = d.v[i] >> 30;
+            d.v[i] &= 0x3FFFFFFF;
+        }
+        d.v[8] += c;
+        const int32_t dneg2 = d.v[8] >> 31;
+        c = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {                                  // still negative: add p once more -> [0, p)
+            d.v[i] += (P.v[i] & dneg2) + c;
+            c = i < 8 ? d.v[i] >> 30 : 0;
+            if (i < 8) d.v[i] &= 0x3FFFFFFF;
+        }
+        Fp y;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {  // 9 x 30 -> 8 x 32
+            const int bit = 32 * k, i = bit / 30, sh = bit % 30;
+            uint64_t two = (uint64_t)(uint32_t)d.v[i] | ((uint64_t)(uint32_t)d.v[i + 1] << 30);
+            y.v[k] = (uint32_t)(two >> sh);
+        }
+        Fp r3;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r3.v[i] = PR::R3(i);
+        return y * r3;  // (value * R)^-1 * R^3 / R = value^-1 * R
+    }
+    // what the kernels call where one inversion sits alone on a critical path
+    G16_HD Fp inverse_fast() const {
+#ifdef G16_INV_BGCD
+        return inverse_bgcd();
+#else
+        return inverse_safegcd();
+#endif
+    }
 };
 
 typedef Fp<FrParams> Fr;
@@ -652,8 +887,8 @@ struct Fq2 {
         Fq n = (c0.sqr() + c1.sqr()).inverse();
         return Fq2{c0 * n, (c1 * n).neg()};
     }
-    G16_HD_NOINLINE Fq2 inverse_bgcd() const {  // same value, low-latency Fq inversion
-        Fq n = (c0.sqr() + c1.sqr()).inverse_bgcd();
+    G16_HD_NOINLINE Fq2 inverse_fast() const {  // same value, low-latency Fq inversion
+        Fq n = (c0.sqr() + c1.sqr()).inverse_fast();
         return Fq2{c0 * n, (c1 * n).neg()};
     }
 };

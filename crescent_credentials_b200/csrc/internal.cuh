@@ -72,6 +72,7 @@ struct MsmScratch {
     // -- point stage: per MSM ---------------------------------------------------------------------------------------------
     void *ba_buf_a = nullptr, *ba_buf_b = nullptr;  // affine points after odd / even levels
     void *ba_pre = nullptr, *ba_T = nullptr, *ba_Q = nullptr;  // Fq: prefix products per slot, thread totals, their inverses
+    void* ba_den = nullptr;                                    // Fq: per-slot denominator norms (G2 only)
     void* partial = nullptr;           // XYZZ per task
     void* bucket_sum = nullptr;        // XYZZ per bucket
     void* chunk_sum = nullptr;         // XYZZ per chunk
@@ -113,6 +114,14 @@ struct VerifyKeyDev {
     size_t cap = 0;
 };
 
+// one captured launch sequence (api.cu: run_graphed)
+struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t key = ~0ull;     // what the sequence depends on (reduction, h source, option epoch)
+    uint64_t launches = 0;    // kernel launches one replay stands for
+    int seen = 0;             // runs with this key so far (first eager, second captured)
+};
+
 }  // namespace g16
 
 struct g16_ctx {
@@ -121,6 +130,14 @@ struct g16_ctx {
     bool own_main = false;
     cudaStream_t side[g16::kSideStreams] = {};
     cudaEvent_t ev_fork = nullptr;
+    cudaStream_t wire = nullptr;  // root of the z-only MSM chains (forked from main, joined back at the end of a shard run)
+    cudaEvent_t ev_wfork = nullptr, ev_wire_done = nullptr, ev_pre = nullptr;
+    g16::GraphSlot graphs[4];     // FULL / WIRE / WM / H launch sequences
+    uint64_t graph_epoch = 1;     // bumped by everything that changes a sequence (options, key, R1CS)
+    bool capturing = false;
+    uint64_t graph_replays = 0, graph_captures = 0, graph_fallbacks = 0;
+    int opt_graph = 1;            // replay the launch sequences as CUDA graphs (0: eager launches)
+    void* h_proof = nullptr;      // page-locked landing zone of the proof read-back
     cudaEvent_t ev_scale[2] = {};
     cudaEvent_t ev_join[g16::kSideStreams] = {};
     cudaEvent_t ev_t[16] = {};
@@ -153,6 +170,8 @@ struct g16_ctx {
     g16::G2Affine beta_g2, delta_g2, b2_0;
     void* d_partial = nullptr;  // g16_partial on the device
     void* d_small = nullptr;    // small device scratch for assembly
+    void* h_scalars = nullptr;  // page-locked staging of (r, s, rs) (assemble.cu), two alternating slots
+    int h_scalars_slot = 0;
     void* d_asm_tables = nullptr;  // assemble.cu: per-key fixed-base tables of the (r, s)-only scalar multiplications
     int opt_asm_tables = 1;        // 0: the single-lane double-and-add k_assemble_pre
     g16_timings tm = {};
@@ -167,16 +186,10 @@ struct g16_ctx {
     bool wm_alone = true;      // state of the auto choice for the transforms being queued right now
     int opt_split_chains = 1;  // the MSM that reuses a digit stage runs beside the one that built it, not after it
     int opt_wm_priority = 0;   // witness map + h MSM on the internal high-priority stream
-    int opt_ba_prefetch = 0;   // 1: k_ba_add_pf (next slot's operands in flight as cp.async), 2: prefetch.global.L2 of the next
-                               // slot's table lines.  Both measured SLOWER than the plain kernel (level 0 is bound by random
-                               // 128-byte DRAM granules, not by latency): kept for the A/B record only
     cudaStream_t hi = nullptr;  // high-priority twin of main
     cudaEvent_t ev_dig[2] = {}, ev_hi = nullptr;
     bool share_al = false, share_b = false;  // l reuses a's digit stage / b_g2 reuses b_g1's
     cudaStream_t sh_wm_stream = nullptr;      // stream the witness map of the open shard run was queued on
-    uint32_t sh_join_mask = 0;                // ev_join[] entries shard_finish has to wait for
-    int sh_nchains = 0;                       // state handed from shard_begin to shard_finish (api.cu)
-    bool sh_scaled[2] = {false, false};
     bool shard_open = false;
     bool tm_stale = false;  // events of a *_dev shard run not yet read into tm
     cudaEvent_t ev_acc[10] = {};
@@ -268,13 +281,16 @@ int msm_can_share(g16_ctx* ctx, const MsmBases* a, const MsmBases* b, size_t max
 int fixed_base_dev(g16_ctx* ctx, int group, const Fr* scalars_dev, size_t n, void* out_pts_dev, cudaStream_t st);
 
 // assemble.cu -----------------------------------------------------------------------------------------------------------
-int assemble_pre(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, cudaStream_t st);
+int assemble_set_scalars(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, cudaStream_t st);  // (r, s, rs) -> device, stream-ordered
+int assemble_pre(g16_ctx* ctx, cudaStream_t st);
 int assemble_build_tables(g16_ctx* ctx, cudaStream_t st);
 G1Affine g1_generator();
 G2Affine g2_generator();
-// out = k * in for one G1 XYZZ point on the device (k: Montgomery Fr on the host)
-int scale_point_dev(g16_ctx* ctx, const void* in_xyzz, const uint64_t* k_mont, void* out_xyzz, cudaStream_t st);
-int assemble_proof(g16_ctx* ctx, const void* partials_dev, int count, g16_proof* out, cudaStream_t st);
+// out = k * in for one G1 XYZZ point on the device; k = r (which = 0) or s (which = 1) of the scalars set by assemble_set_scalars
+int scale_point_dev(g16_ctx* ctx, const void* in_xyzz, int which, void* out_xyzz, cudaStream_t st);
+// k_assemble_post + the read-back into the context's page-locked block (stream-ordered); _read unpacks it after a synchronise
+int assemble_proof_queue(g16_ctx* ctx, const void* partials_dev, int count, cudaStream_t st);
+void assemble_proof_read(g16_ctx* ctx, g16_proof* out);
 int xyzz_to_affine_host(g16_ctx* ctx, int group, const void* xyzz_dev, uint64_t* out, int* out_inf, cudaStream_t st);
 // sum of `count` XYZZ points -> one affine point on the host (the combine step of a point-range sharded MSM)
 int sum_partials_to_affine_host(g16_ctx* ctx, int group, const void* xyzz_dev, int count, uint64_t* out, int* out_inf, cudaStream_t st);

@@ -138,7 +138,7 @@ template <class F, bool L0>
 __global__ void __launch_bounds__(128)
     k_ba_products(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ in_start,
                   const uint32_t* __restrict__ in_cnt, const uint32_t* __restrict__ out_off, size_t nbuckets,
-                  const uint32_t* __restrict__ tb_first, Fq* __restrict__ pre, Fq* __restrict__ T) {
+                  const uint32_t* __restrict__ tb_first, Fq* __restrict__ pre, Fq* __restrict__ T, Fq* __restrict__ den_out) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = out_off[nbuckets];
     const size_t o0 = t * kBaK;
@@ -170,7 +170,12 @@ __global__ void __launch_bounds__(128)
                 Affine<F> p1 = ba_load<F, L0>(src, vals, s), p2 = ba_load<F, L0>(src, vals, s + 1);
                 kind = ba_classify(p1, p2, d);
             }
-            if (kind != BA_TRIVIAL) run = run * BaField<F>::den(d);
+            if (kind != BA_TRIVIAL) {
+                const Fq den = BaField<F>::den(d);
+                // G2: the Fq norm costs two squarings; k_ba_add reads it back instead of recomputing it (G1: den is d itself)
+                if (sizeof(F) != sizeof(Fq)) st_vec(den_out + o, den);
+                run = run * den;
+            }
         }
         st_vec(pre + o, run);
     }
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(128)
     }
     // acc = product of all 32 lanes (identical in every lane); one inversion per warp
     Fq inv;
-    if (lane == 31) inv = acc.inverse_bgcd();
+    if (lane == 31) inv = acc.inverse_fast();
     inv = shfl_fq(inv, 31);
     // down-sweep: inverse of a block's product = inverse of the merged product * the sibling's product
 #pragma unroll
@@ -238,14 +243,12 @@ static int ba_invert(g16_ctx* ctx, const uint32_t* out_off, size_t nbuckets, siz
     return G16_OK;
 }
 
-// PF (level 0 only): while slot o is computed, the two table lines of slot o - 1 (same bucket) are requested into L2
-// (prefetch.global.L2: no register, no scoreboard), so that the gather of the next iteration finds them on chip.
-template <class F, bool L0, bool PF = false>
+template <class F, bool L0>
 __global__ void __launch_bounds__(128)
     k_ba_add(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ in_start,
              const uint32_t* __restrict__ in_cnt, const uint32_t* __restrict__ out_off, size_t nbuckets,
              const uint32_t* __restrict__ tb_last, const Fq* __restrict__ pre, const Fq* __restrict__ Tinv,
-             Affine<F>* __restrict__ out) {
+             Affine<F>* __restrict__ out, const Fq* __restrict__ den_in) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = out_off[nbuckets];
     const size_t o0 = t * kBaK;
@@ -267,11 +270,6 @@ __global__ void __launch_bounds__(128)
         uint32_t i = o - g_off;
         uint32_t s = s_base + 2 * i;
         Affine<F> p1 = ba_load<F, L0>(src, vals, s);
-        if (L0 && PF && i > 0 && o != (uint32_t)o0) {
-            const uint32_t ra = vals[s - 2], rb = vals[s - 1];
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (ra & ~kNegBit)));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (rb & ~kNegBit)));
-        }
         if (2 * i + 1 < s_cnt) {
             Affine<F> p2 = ba_load<F, L0>(src, vals, s + 1);
             F d;
@@ -279,9 +277,16 @@ __global__ void __launch_bounds__(128)
             if (kind == BA_TRIVIAL) {
                 p1 = ba_trivial_sum(p1, p2);
             } else {
-                Fq den = BaField<F>::den(d);
+                Fq den = sizeof(F) == sizeof(Fq) ? BaField<F>::den(d) : ld_vec(den_in + o);  // G2: the norm k_ba_products stored
+#ifdef G16_BA_MUL2
+                // the two products that hang off the running inverse are independent: row-interleaved (four carry chains)
+                Fq prefix = (o == (uint32_t)o0) ? Fq::one() : ld_vec(pre + o - 1);
+                Fq inv_den;
+                Fq::mul_cios2(run, prefix, run, den, inv_den, run);
+#else
                 Fq inv_den = (o == (uint32_t)o0) ? run : run * ld_vec(pre + o - 1);
                 run = run * den;
+#endif
                 F inv_d = BaField<F>::inv(d, inv_den);
                 F num;
                 if (kind == BA_ADD) {
@@ -301,143 +306,6 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-// ---- k_ba_add with the next slot's operands in flight -------------------------------------------------------------------
-// ncu on k_ba_add (level 0): the top stall is long_scoreboard -- every slot starts with two gathered points and one prefix
-// product, and a thread has nothing else to do until they arrive.  This variant keeps the loop and the arithmetic of k_ba_add
-// and moves the loads one slot ahead: while slot o is computed, the operands of slot o - 1 travel global -> shared memory as
-// cp.async (LDGSTS: no registers held, no scoreboard wait), into a per-thread staging area of 2 points + 1 prefix laid out
-// [16-byte chunk][thread] (conflict-free).  One buffer is enough: slot o's operands are copied to registers before the
-// copies of slot o - 1 are issued.  The sorted references of level 0 are read one slot further ahead still (slot o - 2).
-__device__ __forceinline__ void cp_async16(uint4* smem_dst, const uint4* gsrc) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-struct BaSlot {
-    uint32_t s, r1, r2;  // first input position; level 0: the two sorted references (sign in the top bit)
-    bool pair;           // false: a lone point that is carried up unchanged
-};
-
-template <class F, bool L0>
-__global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fq) ? 6 : 3)
-    k_ba_add_pf(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ in_start,
-                const uint32_t* __restrict__ in_cnt, const uint32_t* __restrict__ out_off, size_t nbuckets,
-                const uint32_t* __restrict__ tb_last, const Fq* __restrict__ pre, const Fq* __restrict__ Tinv,
-                Affine<F>* __restrict__ out) {
-    constexpr int PC = sizeof(Affine<F>) / 16;  // 16-byte chunks per point
-    extern __shared__ uint4 ba_stage[];         // [2 * PC + 2][128]
-    uint4* const stage = ba_stage + threadIdx.x;
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t total = out_off[nbuckets];
-    const size_t o0 = t * kBaK;
-    if (o0 >= total) return;
-    const uint32_t o_first = (uint32_t)o0;
-    const uint32_t o_last = (uint32_t)(o0 + kBaK < total ? o0 + kBaK : total) - 1;
-    uint32_t g = tb_last[t];
-    uint32_t g_off = out_off[g];
-    uint32_t s_base = in_start[g];
-    uint32_t s_cnt = in_cnt ? in_cnt[g] : in_start[g + 1] - s_base;
-    auto locate = [&](uint32_t o) {  // called with descending o
-        while (o < g_off) {
-            g--;
-            g_off = out_off[g];
-            s_base = in_start[g];
-            s_cnt = in_cnt ? in_cnt[g] : in_start[g + 1] - s_base;
-        }
-        uint32_t i = o - g_off;
-        BaSlot d;
-        d.s = s_base + 2 * i;
-        d.pair = 2 * i + 1 < s_cnt;
-        d.r1 = d.r2 = 0;
-        if (L0) {
-            d.r1 = vals[d.s];
-            if (d.pair) d.r2 = vals[d.s + 1];
-        }
-        return d;
-    };
-    auto issue = [&](const BaSlot& d, uint32_t o) {
-        const uint4* a = reinterpret_cast<const uint4*>(L0 ? src + (d.r1 & ~kNegBit) : src + d.s);
-#pragma unroll
-        for (int c = 0; c < PC; c++) cp_async16(stage + c * 128, a + c);
-        if (d.pair) {
-            const uint4* b = reinterpret_cast<const uint4*>(L0 ? src + (d.r2 & ~kNegBit) : src + d.s + 1);
-#pragma unroll
-            for (int c = 0; c < PC; c++) cp_async16(stage + (PC + c) * 128, b + c);
-            if (o != o_first) {
-                const uint4* q = reinterpret_cast<const uint4*>(pre + o - 1);
-                cp_async16(stage + (2 * PC) * 128, q);
-                cp_async16(stage + (2 * PC + 1) * 128, q + 1);
-            }
-        }
-        cp_async_commit();
-    };
-    auto staged_point = [&](int base, uint32_t ref) {
-        Affine<F> p;
-        uint4* d = reinterpret_cast<uint4*>(&p);
-#pragma unroll
-        for (int c = 0; c < PC; c++) d[c] = stage[(base + c) * 128];
-        if (L0 && (ref & kNegBit)) p.y = p.y.neg();
-        return p;
-    };
-
-    Fq run = ld_vec(Tinv + t);
-    uint32_t o = o_last;
-    BaSlot cur = locate(o);
-    issue(cur, o);
-    BaSlot nxt = cur;
-    if (o != o_first) nxt = locate(o - 1);
-#pragma unroll 1
-    for (;;) {
-        cp_async_wait_all();
-        Affine<F> p1 = staged_point(0, cur.r1);
-        Affine<F> p2 = p1;
-        Fq prefix = Fq::one();
-        if (cur.pair) {
-            p2 = staged_point(PC, cur.r2);
-            if (o != o_first) {
-                uint4* d = reinterpret_cast<uint4*>(&prefix);
-                d[0] = stage[(2 * PC) * 128];
-                d[1] = stage[(2 * PC + 1) * 128];
-            }
-        }
-        BaSlot nn = nxt;
-        if (o != o_first) {
-            issue(nxt, o - 1);  // the staging area is free again: its contents are in registers
-            if (o - 1 != o_first) nn = locate(o - 2);
-        }
-        if (cur.pair) {
-            F d;
-            int kind = ba_classify(p1, p2, d);
-            if (kind == BA_TRIVIAL) {
-                p1 = ba_trivial_sum(p1, p2);
-            } else {
-                Fq den = BaField<F>::den(d);
-                Fq inv_den = (o == o_first) ? run : run * prefix;
-                run = run * den;
-                F inv_d = BaField<F>::inv(d, inv_den);
-                F num;
-                if (kind == BA_ADD) {
-                    num = p2.y - p1.y;
-                } else {
-                    F xx = p1.x.sqr();
-                    num = xx.dbl() + xx;
-                }
-                F lam = num * inv_d;
-                F x3 = lam.sqr() - p1.x - p2.x;
-                p1.y = lam * (p1.x - x3) - p1.y;
-                p1.x = x3;
-            }
-        }
-        st_vec(out + o, p1);
-        if (o == o_first) break;
-        o--;
-        cur = nxt;
-        nxt = nn;
-    }
-}
-
 // ---- host side ----------------------------------------------------------------------------------------------------------------
 size_t ba_level_cap(size_t items, size_t nbuckets, int level) {
     size_t cap = items;
@@ -454,6 +322,8 @@ void ba_free(MsmScratch* sc) {
     dev_free(sc->ba_pre);
     dev_free(sc->ba_T);
     dev_free(sc->ba_Q);
+    dev_free(sc->ba_den);
+    sc->ba_den = nullptr;
     sc->ba_start0 = sc->ba_lvl = sc->ba_tb = nullptr;
     sc->ba_buf_a = sc->ba_buf_b = nullptr;
     sc->ba_pre = sc->ba_T = sc->ba_Q = nullptr;
@@ -481,6 +351,10 @@ int ba_alloc(g16_ctx* ctx, int group, MsmScratch* sc, size_t items, size_t nbuck
     sc->ba_T = p;
     G16_TRY(dev_alloc(ctx, &p, threads + 1));
     sc->ba_Q = p;
+    if (group == 2) {  // per-slot Fq norms of the G2 denominators, written by k_ba_products and read back by k_ba_add
+        G16_TRY(dev_alloc(ctx, &p, cap1));
+        sc->ba_den = p;
+    }
     return G16_OK;
 }
 
@@ -500,7 +374,6 @@ template <class F>
 static int ba_run_levels_t(g16_ctx* ctx, const MsmBases* mb, MsmScratch* sc, const MsmScratch* dg, size_t items, size_t nbuckets,
                            int levels, const void** out_pts, cudaStream_t st, cudaEvent_t add0_ev0, cudaEvent_t add0_ev1) {
     const Affine<F>* src = (const Affine<F>*)mb->pts;
-    const size_t stage_bytes = (2 * sizeof(Affine<F>) / 16 + 2) * 128 * sizeof(uint4);  // k_ba_add_pf: 2 points + 1 prefix per thread
     for (int k = 0; k < levels; k++) {
         size_t cap = ba_level_cap(items, nbuckets, k + 1);
         size_t threads = (cap + kBaK - 1) / kBaK;
@@ -514,30 +387,21 @@ static int ba_run_levels_t(g16_ctx* ctx, const MsmBases* mb, MsmScratch* sc, con
         Fq* pre = (Fq*)sc->ba_pre;
         Fq* T = (Fq*)sc->ba_T;
         Fq* Q = (Fq*)sc->ba_Q;
+        Fq* den = (Fq*)sc->ba_den;  // G2 only
         if (k == 0) {
-            G16_LAUNCH(ctx, (k_ba_products<F, true>), grid, 128, 0, st, src, dg->s_vals, in_start, in_cnt, out_off, nbuckets, tb_first, pre, T);
+            G16_LAUNCH(ctx, (k_ba_products<F, true>), grid, 128, 0, st, src, dg->s_vals, in_start, in_cnt, out_off, nbuckets, tb_first, pre, T,
+                       den);
             G16_TRY(ba_invert(ctx, out_off, nbuckets, threads, T, Q, st));
             if (add0_ev0) G16_CUDA(ctx, cudaEventRecord(add0_ev0, st));
-            if (ctx->opt_ba_prefetch == 1)
-                G16_LAUNCH(ctx, (k_ba_add_pf<F, true>), grid, 128, stage_bytes, st, src, dg->s_vals, in_start, in_cnt, out_off, nbuckets,
-                           tb_last, (const Fq*)pre, (const Fq*)Q, dst);
-            else if (ctx->opt_ba_prefetch == 2)
-                G16_LAUNCH(ctx, (k_ba_add<F, true, true>), grid, 128, 0, st, src, dg->s_vals, in_start, in_cnt, out_off, nbuckets, tb_last,
-                           (const Fq*)pre, (const Fq*)Q, dst);
-            else
-                G16_LAUNCH(ctx, (k_ba_add<F, true>), grid, 128, 0, st, src, dg->s_vals, in_start, in_cnt, out_off, nbuckets, tb_last,
-                           (const Fq*)pre, (const Fq*)Q, dst);
+            G16_LAUNCH(ctx, (k_ba_add<F, true>), grid, 128, 0, st, src, dg->s_vals, in_start, in_cnt, out_off, nbuckets, tb_last,
+                           (const Fq*)pre, (const Fq*)Q, dst, (const Fq*)den);
             if (add0_ev1) G16_CUDA(ctx, cudaEventRecord(add0_ev1, st));
         } else {
             G16_LAUNCH(ctx, (k_ba_products<F, false>), grid, 128, 0, st, src, (const uint32_t*)nullptr, in_start, in_cnt, out_off, nbuckets,
-                       tb_first, pre, T);
+                       tb_first, pre, T, den);
             G16_TRY(ba_invert(ctx, out_off, nbuckets, threads, T, Q, st));
-            if (ctx->opt_ba_prefetch == 1)
-                G16_LAUNCH(ctx, (k_ba_add_pf<F, false>), grid, 128, stage_bytes, st, src, (const uint32_t*)nullptr, in_start, in_cnt, out_off,
-                           nbuckets, tb_last, (const Fq*)pre, (const Fq*)Q, dst);
-            else
-                G16_LAUNCH(ctx, (k_ba_add<F, false>), grid, 128, 0, st, src, (const uint32_t*)nullptr, in_start, in_cnt, out_off, nbuckets,
-                           tb_last, (const Fq*)pre, (const Fq*)Q, dst);
+            G16_LAUNCH(ctx, (k_ba_add<F, false>), grid, 128, 0, st, src, (const uint32_t*)nullptr, in_start, in_cnt, out_off, nbuckets,
+                           tb_last, (const Fq*)pre, (const Fq*)Q, dst, (const Fq*)den);
         }
         src = dst;
     }

@@ -106,7 +106,7 @@ struct Fq6 {
         Fq2 t1 = fq2_mul_xi(c2.sqr()) - c0 * c1;
         Fq2 t2 = c1.sqr() - c0 * c2;
         Fq2 d = c0 * t0 + fq2_mul_xi(c2 * t1 + c1 * t2);
-        Fq2 di = d.inverse_bgcd();
+        Fq2 di = d.inverse_fast();
         return Fq6{t0 * di, t1 * di, t2 * di};
     }
 };

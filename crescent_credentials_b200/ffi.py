@@ -30,7 +30,7 @@ EXPORTS = [
     "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count", "g16_set_option",
     "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare", "g16_get_msm_stats", "g16_ctx_load_pk_ranges",
     "g16_prove_shard_begin_dev", "g16_prove_shard_finish_dev", "g16_copy_h_dev",
-    "g16_upload_witness_async", "g16_msm_copy_result_dev", "g16_msm_combine_dev",
+    "g16_upload_witness_async", "g16_msm_copy_result_dev", "g16_msm_combine_dev", "g16_graph_stats",
     "g16_ctx_load_vk", "g16_vk_alpha_beta", "g16_prepare_inputs", "g16_verify_batch", "g16_verify_batch_prepared",
     "g16_verify_batch_dev", "g16_pairing", "g16_host_alloc", "g16_host_free",
 ]
@@ -145,6 +145,7 @@ def load_library() -> C.CDLL:
     lib.g16_msm_run_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]
     lib.g16_msm_copy_result_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.g16_msm_combine_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.g16_graph_stats.argtypes = [C.c_void_p, C.c_void_p]
     lib.g16_ntt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int]
     lib.g16_ntt_dev.argtypes = lib.g16_ntt.argtypes
     lib.g16_field_op.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -300,6 +301,11 @@ class Context:
         v = C.c_double(0)
         self.check(self.lib.g16_bench_int_pipe(self.h, which, C.byref(v)))
         return v.value
+
+    def graph_stats(self) -> dict:
+        out = np.zeros(3, dtype=np.uint64)
+        self.check(self.lib.g16_graph_stats(self.h, _ptr(out)))
+        return {"replays": int(out[0]), "captures": int(out[1]), "fallbacks": int(out[2])}
 
     def launch_count(self) -> int:
         return int(self.lib.g16_launch_count(self.h))

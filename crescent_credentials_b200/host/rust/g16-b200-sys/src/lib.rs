@@ -136,6 +136,63 @@ impl B200Prover {
 }
 impl Drop for B200Prover { fn drop(&mut self) { unsafe { g16_ctx_destroy(self.ctx) } } }
 
+// ---- prover_for: the per-(pk, matrices) cache the fork's prover.rs calls ---------------------------
+// `create_proof_with_reduction_and_matrices` receives `&ProvingKey` and `&ConstraintMatrices` on every call and keeps nothing
+// between calls (SURVEY 8b "Ownership"); the device copies must outlive the call.  Identity cannot be the address (a key that
+// was dropped and reloaded may land elsewhere, and another key may land on the old address), so the cache is keyed on a CONTENT
+// fingerprint: lengths plus a 64-bit FNV-1a over the first / last / strided sample of every query and of the matrices'
+// coefficient words -- cheap (a few thousand words per call) and collision-safe for the handful of keys a process ever holds.
+// One entry per fingerprint; a Mutex per entry serialises proofs on that context (the C side locks as well).
+use std::collections::HashMap;
+use std::sync::{Arc, Mutex, OnceLock};
+
+#[derive(Clone, Copy, PartialEq, Eq, Hash)]
+pub struct Fingerprint(u64, usize, usize);
+
+fn fnv(h: &mut u64, words: &[u64]) { for w in words { *h = (*h ^ *w).wrapping_mul(0x100000001b3); } }
+fn sample_g1(h: &mut u64, v: &[G1Affine]) {
+    let n = v.len();
+    let step = (n / 64).max(1);
+    for i in (0..n).step_by(step).chain(n.saturating_sub(1)..n) { let mut o = Vec::with_capacity(8); pack_g1(&v[i], &mut o); fnv(h, &o); }
+}
+
+/// Fingerprint of (pk, matrices) -- the cache key of `prover_for`.
+pub fn fingerprint(a: &[G1Affine], b1: &[G1Affine], h_query: &[G1Affine], l: &[G1Affine], delta_g1: &G1Affine,
+                   m: &ConstraintMatrices<Fr>) -> Fingerprint {
+    let mut h = 0xcbf29ce484222325u64;
+    sample_g1(&mut h, a); sample_g1(&mut h, b1); sample_g1(&mut h, h_query); sample_g1(&mut h, l); sample_g1(&mut h, &[*delta_g1]);
+    fnv(&mut h, &[m.num_constraints as u64, m.num_instance_variables as u64, m.num_witness_variables as u64,
+                  m.a_num_non_zero as u64, m.b_num_non_zero as u64, m.c_num_non_zero as u64]);
+    for rows in [&m.a, &m.b, &m.c] {
+        let step = (rows.len() / 256).max(1);
+        for row in rows.iter().step_by(step) { for (c, j) in row { fnv(&mut h, &fr_limbs(c)); fnv(&mut h, &[*j as u64]); } }
+    }
+    Fingerprint(h, a.len(), h_query.len())
+}
+
+static PROVERS: OnceLock<Mutex<HashMap<Fingerprint, Arc<Mutex<B200Prover>>>>> = OnceLock::new();
+
+/// The persistent prover for this (pk, matrices): created, loaded (key upload + window tables + CSR upload: seconds, once) and
+/// cached on first use, reused by every later proof.  `device` < 0 picks device 0.  Called by forks/groth16/src/b200.rs.
+#[allow(clippy::too_many_arguments)]
+pub fn prover_for(device: i32, alpha_g1: &G1Affine, beta_g1: &G1Affine, delta_g1: &G1Affine, beta_g2: &G2Affine, delta_g2: &G2Affine,
+                  a: &[G1Affine], b1: &[G1Affine], b2: &[G2Affine], h_query: &[G1Affine], l: &[G1Affine],
+                  m: &ConstraintMatrices<Fr>) -> Result<Arc<Mutex<B200Prover>>, SynthesisError> {
+    let key = fingerprint(a, b1, h_query, l, delta_g1, m);
+    let map = PROVERS.get_or_init(|| Mutex::new(HashMap::new()));
+    let mut guard = map.lock().unwrap();
+    if let Some(p) = guard.get(&key) { return Ok(p.clone()); }
+    let mut p = B200Prover::new(device.max(0));
+    p.load_matrices(m)?;                                   // PolynomialDegreeTooLarge surfaces here (r1cs_to_qap.rs:156-157)
+    p.load_pk(alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2, a, b1, b2, h_query, l);
+    let p = Arc::new(Mutex::new(p));
+    guard.insert(key, p.clone());
+    Ok(p)
+}
+
+/// Drops every cached context (frees the device copies); e.g. between circuits in a long-lived service.
+pub fn clear_provers() { if let Some(m) = PROVERS.get() { m.lock().unwrap().clear(); } }
+
 /// Persistent GPU verifier for one VerifyingKey (forks/groth16/src/verifier.rs): `verify_proofs` checks n (proof, inputs)
 /// pairs per call, one device thread per proof, and returns the reference's verdict for each.
 pub struct B200Verifier { ctx: *mut c_void, inputs: usize }

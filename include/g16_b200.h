@@ -201,12 +201,16 @@ int g16_get_timings(g16_ctx* ctx, g16_timings* out);
  * "wm_priority" = 1 runs the witness map and the h MSM on a high-priority stream (default 0),
  * "ntt_radix4" = 0 / 1 forces the radix-2 / radix-4 transform passes (default -1: radix-4 only when no MSM runs beside),
  * "spmv_sell" = 0 selects the row-per-thread CSR kernel instead of the sliced-ELL one (default 1),
- * "ba_prefetch" = 1 / 2 selects the cp.async / L2-prefetch variants of k_ba_add (default 0; both measured slower),
+ * "graph" = 0 queues every launch of a proof eagerly instead of replaying the captured launch sequences as CUDA graphs
+ *   (default 1; the first run of a sequence is always eager, the second is captured),
  * "asm_tables" = 0 computes the (r, s)-only points of the assembly with one lane per scalar multiplication instead of the
  *   per-key fixed-base tables (default 1; matters for small circuits only: 4.4 ms -> 0.3 ms of latency),
  * "verify_occupancy" = 8 / 12 / 16 selects the k_verify build for that many resident warps per SM (255 / 168 / 128 registers).
  * No option changes a result bit.  Unknown keys return G16_ERR_BAD_ARG. */
 int g16_set_option(g16_ctx* ctx, const char* key, int value);
+/* CUDA-graph replay counters: out[0] = graph launches so far, out[1] = launch sequences captured, out[2] = captures that failed
+ * (after one the context queues its launches eagerly).  g16_launch_count counts the kernels a replay stands for. */
+int g16_graph_stats(const g16_ctx* ctx, uint64_t out[3]);
 
 /* ---- building blocks (parity hooks and the synthetic sweep) ------------------------------------------------------- */
 /* Sigma scalars[i] * points[i]; scalars Montgomery Fr; result affine Montgomery (+ infinity flag). */

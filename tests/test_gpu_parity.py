@@ -263,9 +263,8 @@ def test_msm_window_sizes(gpu_ctx, c):
     assert g.g1_from_mont(out, inf) == o.G1.to_affine(o.G1.msm(pts, sc))
 
 
-@pytest.mark.parametrize("prefetch", [0, 1, 2])
 @pytest.mark.parametrize("levels", [0, 1, 2, 3, 8])
-def test_msm_batched_affine_levels(gpu_ctx, levels, prefetch):
+def test_msm_batched_affine_levels(gpu_ctx, levels):
     """Every split between batched-affine levels and the XYZZ tail gives the same group element (G1 and G2), including
     infinity points, repeated points (tangent case), P + (-P) pairs and one heavily loaded bucket (equal scalars)."""
     n = 260
@@ -278,7 +277,6 @@ def test_msm_batched_affine_levels(gpu_ctx, levels, prefetch):
         sc[i] = 3                                  # one bucket with 130 points: survivors go through the task path or the
                                                    # one-thread tail depending on the number of levels
     gpu_ctx.set_option("ba_levels", levels)
-    gpu_ctx.set_option("ba_prefetch", prefetch)
     try:
         out, inf = gpu_ctx.msm(1, g.g1_points_to_mont(pts), g.fr_to_mont(sc))
         assert g.g1_from_mont(out, inf) == o.G1.to_affine(o.G1.msm(pts, sc))
@@ -294,7 +292,6 @@ def test_msm_batched_affine_levels(gpu_ctx, levels, prefetch):
         assert g.g2_from_mont(out, inf) == o.G2.to_affine(o.G2.msm(p2, s2))
     finally:
         gpu_ctx.set_option("ba_levels", -1)
-        gpu_ctx.set_option("ba_prefetch", 0)
 
 
 @pytest.mark.parametrize("share,levels", [(0, 0), (0, 5), (1, 0), (1, 5)])

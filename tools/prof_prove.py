@@ -23,7 +23,7 @@ ap.add_argument("--serialize", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--ba-levels", type=int, default=-1)
 ap.add_argument("--share-digits", type=int, default=1)
-ap.add_argument("--opt", nargs="*", default=[], help="library options, key=value (e.g. ba_prefetch=0)")
+ap.add_argument("--opt", nargs="*", default=[], help="library options, key=value (e.g. graph=0)")
 args = ap.parse_args()
 tstream = torch.cuda.Stream()
 torch.cuda.set_stream(tstream)

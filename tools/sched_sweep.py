@@ -18,7 +18,7 @@ from bench import build_problem  # noqa: E402
 from crescent_credentials_b200 import ffi  # noqa: E402
 from crescent_credentials_b200 import groth16 as g  # noqa: E402
 
-DEFAULTS = {"split_chains": 1, "wm_priority": 0, "ntt_radix4": -1, "spmv_sell": 1, "ba_prefetch": 0, "serialize": 0}
+DEFAULTS = {"split_chains": 1, "wm_priority": 0, "ntt_radix4": -1, "spmv_sell": 1, "serialize": 0}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="S-rs256")
