@@ -1188,6 +1188,7 @@ int g16_set_option(g16_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "split_chains")) ctx->opt_split_chains = value;
     else if (!strcmp(key, "ntt_radix4")) ctx->opt_ntt_radix4 = value;
     else if (!strcmp(key, "spmv_sell")) ctx->opt_spmv_sell = value;
+    else if (!strcmp(key, "ntt_batch")) ctx->opt_ntt_batch = value;
     else if (!strcmp(key, "wm_priority")) ctx->opt_wm_priority = value;
     else if (!strcmp(key, "verify_occupancy")) ctx->opt_verify_occupancy = value;
     else if (!strcmp(key, "asm_tables")) ctx->opt_asm_tables = value;

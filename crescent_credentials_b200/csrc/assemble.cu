@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(160) k_assemble_pre_tables(const AsmTables* __
 __global__ void k_scale_point(const G1XYZZ* __restrict__ in, const Scalar256* __restrict__ k, G1XYZZ* __restrict__ out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const Scalar256 kk = *k;
-        *out = scalar_mul(*in, kk.w);
+        *out = scalar_mul_window(*in, kk.w);
     }
 }
 

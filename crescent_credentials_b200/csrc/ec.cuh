@@ -31,8 +31,10 @@ struct XYZZ {
     }
     G16_HD XYZZ neg() const { return XYZZ{x, y.neg(), zz, zzz}; }
 
-    // doubling, dbl-2008-s-1 with a = 0: 6M + 3S
-    G16_HD_NOINLINE XYZZ dbl() const {
+    // doubling, dbl-2008-s-1 with a = 0: 6M + 3S.  dbl() is a real call (code size); dbl_inl() is the same body inlined, for
+    // the latency-bound single-lane chains (bucket reduction) where the call's trip through local memory costs more than the code
+    G16_HD_NOINLINE XYZZ dbl() const { return dbl_inl(); }
+    G16_HD XYZZ dbl_inl() const {
         if (is_inf()) return *this;
         F u = y.dbl();
         if (u.is_zero()) return inf();
@@ -99,8 +101,9 @@ struct XYZZ {
         zzz = zzz * p3;
     }
 
-    // full addition acc += o (add-2008-s): 12M + 2S
-    G16_HD_NOINLINE void add(const XYZZ& o) {
+    // full addition acc += o (add-2008-s): 12M + 2S.  add() is a real call, add_inl() the same body inlined (see dbl_inl)
+    G16_HD_NOINLINE void add(const XYZZ& o) { add_inl(o); }
+    G16_HD void add_inl(const XYZZ& o) {
         if (o.is_inf()) return;
         if (is_inf()) {
             *this = o;
@@ -155,6 +158,47 @@ G16_HD_NOINLINE XYZZ<F> scalar_mul(const XYZZ<F>& p, const uint32_t* k) {
                 started = true;
             }
         }
+    }
+    return acc;
+}
+
+// Same product for the one place where a fresh-point scalar multiplication is a lone lane's critical path (k_scale_point:
+// s * MSM_a, r * MSM_b1): signed 4-bit windows -- a table of 1P..8P (4 doublings + 3 additions), then 64 x (4 doublings +
+// at most 1 addition) -- with the group operations inlined: ~3100 dependent field products instead of ~4060, none behind a call.
+template <class F>
+G16_HD XYZZ<F> scalar_mul_window(const XYZZ<F>& p, const uint32_t* k) {
+    XYZZ<F> m[9];  // m[d] = d * P
+    m[1] = p;
+    m[2] = p.dbl_inl();
+    m[3] = m[2];
+    m[3].add_inl(p);
+    m[4] = m[2].dbl_inl();
+    m[5] = m[4];
+    m[5].add_inl(p);
+    m[6] = m[3].dbl_inl();
+    m[7] = m[6];
+    m[7].add_inl(p);
+    m[8] = m[4].dbl_inl();
+    // signed digits in [-7, 8], least significant first; a 65th digit takes the last carry
+    signed char digit[65];
+    int carry = 0;
+#pragma unroll 1
+    for (int j = 0; j < 64; j++) {
+        int d = (int)((k[j >> 3] >> (4 * (j & 7))) & 15u) + carry;
+        carry = d > 8;
+        digit[j] = (signed char)(carry ? d - 16 : d);
+    }
+    digit[64] = (signed char)carry;
+    XYZZ<F> acc = XYZZ<F>::inf();
+#pragma unroll 1
+    for (int j = 64; j >= 0; j--) {
+        if (j != 64) {
+#pragma unroll 1
+            for (int t = 0; t < 4; t++) acc = acc.dbl_inl();
+        }
+        const int d = digit[j];
+        if (d > 0) acc.add_inl(m[d]);
+        else if (d < 0) acc.add_inl(m[-d].neg());
     }
     return acc;
 }

@@ -179,6 +179,7 @@ struct g16_ctx {
     int opt_ba_levels = -1;  // batched-affine levels (-1 = default)
     int opt_share_digits = 1;
     int opt_spmv_sell = 1;     // sliced-ELL SpMV (0: row-per-thread CSR kernel)
+    int opt_ntt_batch = 1;     // witness map: a, b, c inverse transforms (and the a, b coset transforms) as one launch per pass
     int opt_ntt_radix4 = -1;   // k_ntt_pass4 (two butterfly levels per shared-memory round trip).  Alone it is faster (witness map
                                // 3.32 vs 3.67 ms) but beside the MSM chains it costs +1.1 ms per proof (profiles/r01_sched_sweep_*):
                                // -1 = auto: radix-4 when nothing runs beside the transforms (stand-alone calls, serialize, a
@@ -253,6 +254,10 @@ int ntt_dif(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* p
 // post_sub (dit, with post): optional vector subtracted after the post scaling (natural order).
 int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* post, const Fr* post_scalar,
             cudaStream_t st, const Fr* pre_mul = nullptr, const Fr* post_sub = nullptr);
+// the same transforms for up to three vectors in one launch per pass (member m of scalar_mask gets post_scalar)
+int ntt_dit_batch(g16_ctx* ctx, Fr* const* data, int count, NttTables* t, bool inverse_root, const Fr* post, const Fr* post_scalar,
+                  unsigned scalar_mask, cudaStream_t st, const Fr* pre_mul = nullptr, const Fr* post_sub = nullptr);
+int ntt_dif_batch(g16_ctx* ctx, Fr* const* data, int count, NttTables* t, bool inverse_root, const Fr* pre, cudaStream_t st);
 int bitrev_permute(g16_ctx* ctx, Fr* data, unsigned log_n, cudaStream_t st);
 int pow_table_dev(g16_ctx* ctx, Fr* out, size_t n, Fr base, Fr scale, cudaStream_t st);
 int ntt_api(g16_ctx* ctx, Fr* data_dev, unsigned log_n, int inverse, int coset, cudaStream_t st);

@@ -119,15 +119,25 @@ int ntt_get_tables(g16_ctx* ctx, unsigned log_n, NttTables** out) {
     return G16_OK;
 }
 
+// Up to three transforms of the same kind run as ONE launch (blockIdx.y = member): the witness map inverts a, b, c together
+// and coset-transforms a, b together.  A 2^21 transform is only 1024 tiles for 148 SMs x 3 resident blocks (2.3 waves: the
+// last wave is a third full); batched, the same passes run 6.9 and 4.6 waves deep and half of the launches disappear.
+struct NttBatch {
+    Fr* data[3];
+    unsigned scalar_mask;  // bit m: member m gets the uniform post_scalar on the last DIT pass
+};
+
 // ---- the shared-memory pass ---------------------------------------------------------------------------------------
 // Levels [s_lo, s_lo + nlev) of a 2^log_n transform.  A tile is 2^nlev rows (the index bits being transformed) by
 // 2^t_log adjacent columns (low index bits, for contiguous global accesses); element (j, c) lives at tile slot j*T + c.
 template <bool DIT>
 __global__ void __launch_bounds__(kNttThreads, 2)
-    k_ntt_pass(Fr* __restrict__ data, const Fr* __restrict__ tw, unsigned log_n, unsigned s_lo, unsigned nlev,
+    k_ntt_pass(NttBatch batch, const Fr* __restrict__ tw, unsigned log_n, unsigned s_lo, unsigned nlev,
                unsigned t_log, const Fr* __restrict__ pre, const Fr* __restrict__ post, Fr post_scalar,
                int has_post_scalar, const Fr* __restrict__ sub) {
     extern __shared__ uint4 smem[];
+    Fr* __restrict__ data = batch.data[blockIdx.y];
+    has_post_scalar = has_post_scalar && ((batch.scalar_mask >> blockIdx.y) & 1u);
     const unsigned tile_log = nlev + t_log;
     const unsigned tile = 1u << tile_log;
     uint4* sm_lo = smem;
@@ -240,10 +250,12 @@ __device__ __forceinline__ Fr tw_ld(const Fr* p) {
 
 template <bool DIT>
 __global__ void __launch_bounds__(kNtt4Threads, 3)
-    k_ntt_pass4(Fr* __restrict__ data, const Fr* __restrict__ tw, unsigned log_n, unsigned s_lo, unsigned nlev,
+    k_ntt_pass4(NttBatch batch, const Fr* __restrict__ tw, unsigned log_n, unsigned s_lo, unsigned nlev,
                 unsigned t_log, const Fr* __restrict__ pre, const Fr* __restrict__ post, Fr post_scalar,
                 int has_post_scalar, const Fr* __restrict__ sub) {
     extern __shared__ uint4 smem[];
+    Fr* __restrict__ data = batch.data[blockIdx.y];
+    has_post_scalar = has_post_scalar && ((batch.scalar_mask >> blockIdx.y) & 1u);
     const unsigned tile_log = nlev + t_log;
     const unsigned tile = 1u << tile_log;
     uint4* sm_lo = smem;
@@ -422,15 +434,21 @@ static int ensure_smem_attr(g16_ctx* ctx) {
     return G16_OK;
 }
 
-int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* post, const Fr* post_scalar,
-            cudaStream_t st, const Fr* pre_mul, const Fr* post_sub) {
+// `count` (<= 3) transforms of the same kind in one launch per pass.  post / pre_mul / post_sub apply to every member (only
+// used with count == 1); post_scalar applies to the members selected by scalar_mask.
+int ntt_dit_batch(g16_ctx* ctx, Fr* const* data, int count, NttTables* t, bool inverse_root, const Fr* post, const Fr* post_scalar,
+                  unsigned scalar_mask, cudaStream_t st, const Fr* pre_mul, const Fr* post_sub) {
     if (post_sub && !post) return set_err(ctx, G16_ERR_BAD_ARG, "ntt_dit: post_sub needs a post table");
+    if (count < 1 || count > 3) return set_err(ctx, G16_ERR_BAD_ARG, "ntt batch of %d", count);
     G16_TRY(ensure_smem_attr(ctx));
     auto passes = plan_passes(t->log_n);
     const Fr* tw = inverse_root ? t->tw_inv : t->tw;
     Fr ps = post_scalar ? *post_scalar : Fr::zero();
+    NttBatch batch{{data[0], count > 1 ? data[1] : nullptr, count > 2 ? data[2] : nullptr}, scalar_mask};
     if (passes.empty()) {  // n == 1: only the element-wise work remains
-        G16_LAUNCH(ctx, k_scale_table, 1, 32, 0, st, data, pre_mul, post, ps, (int)(post != nullptr || post_scalar != nullptr), post_sub, (size_t)1);
+        for (int m = 0; m < count; m++)
+            G16_LAUNCH(ctx, k_scale_table, 1, 32, 0, st, data[m], pre_mul, post, ps,
+                       (int)(post != nullptr || (post_scalar != nullptr && ((scalar_mask >> m) & 1u))), post_sub, (size_t)1);
         return G16_OK;
     }
     for (size_t k = 0; k < passes.size(); k++) {
@@ -438,35 +456,49 @@ int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* p
         bool last = (k + 1 == passes.size());
         size_t blocks = ((size_t)1 << t->log_n) >> (p.nlev + p.t_log);
         size_t smem = ((size_t)1 << (p.nlev + p.t_log)) * 32;
+        dim3 grid((unsigned)blocks, (unsigned)count);
         if (ctx->opt_ntt_radix4 >= 0 ? ctx->opt_ntt_radix4 != 0 : ctx->wm_alone)
-            G16_LAUNCH(ctx, k_ntt_pass4<true>, (unsigned)blocks, kNtt4Threads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
+            G16_LAUNCH(ctx, k_ntt_pass4<true>, grid, kNtt4Threads, smem, st, batch, tw, t->log_n, p.s_lo, p.nlev,
                        p.t_log, k == 0 ? pre_mul : (const Fr*)nullptr, last ? post : (const Fr*)nullptr, ps,
                        (int)(last && post_scalar != nullptr && post == nullptr), last ? post_sub : (const Fr*)nullptr);
         else
-            G16_LAUNCH(ctx, k_ntt_pass<true>, (unsigned)blocks, kNttThreads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
+            G16_LAUNCH(ctx, k_ntt_pass<true>, grid, kNttThreads, smem, st, batch, tw, t->log_n, p.s_lo, p.nlev,
                        p.t_log, k == 0 ? pre_mul : (const Fr*)nullptr, last ? post : (const Fr*)nullptr, ps,
                        (int)(last && post_scalar != nullptr && post == nullptr), last ? post_sub : (const Fr*)nullptr);
     }
     return G16_OK;
 }
+int ntt_dit(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* post, const Fr* post_scalar,
+            cudaStream_t st, const Fr* pre_mul, const Fr* post_sub) {
+    Fr* one[1] = {data};
+    return ntt_dit_batch(ctx, one, 1, t, inverse_root, post, post_scalar, 1u, st, pre_mul, post_sub);
+}
 
-int ntt_dif(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* pre, cudaStream_t st) {
+int ntt_dif_batch(g16_ctx* ctx, Fr* const* data, int count, NttTables* t, bool inverse_root, const Fr* pre, cudaStream_t st) {
+    if (count < 1 || count > 3) return set_err(ctx, G16_ERR_BAD_ARG, "ntt batch of %d", count);
     G16_TRY(ensure_smem_attr(ctx));
     auto passes = plan_passes(t->log_n);
     const Fr* tw = inverse_root ? t->tw_inv : t->tw;
+    NttBatch batch{{data[0], count > 1 ? data[1] : nullptr, count > 2 ? data[2] : nullptr}, 0u};
+    // n == 1: no pass, and every pre table starts with 1 (g^0 / n): nothing to do
     for (size_t k = passes.size(); k-- > 0;) {
         const Pass& p = passes[k];
         bool first = (k + 1 == passes.size());
         size_t blocks = ((size_t)1 << t->log_n) >> (p.nlev + p.t_log);
         size_t smem = ((size_t)1 << (p.nlev + p.t_log)) * 32;
+        dim3 grid((unsigned)blocks, (unsigned)count);
         if (ctx->opt_ntt_radix4 >= 0 ? ctx->opt_ntt_radix4 != 0 : ctx->wm_alone)
-            G16_LAUNCH(ctx, k_ntt_pass4<false>, (unsigned)blocks, kNtt4Threads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
+            G16_LAUNCH(ctx, k_ntt_pass4<false>, grid, kNtt4Threads, smem, st, batch, tw, t->log_n, p.s_lo, p.nlev,
                        p.t_log, first ? pre : (const Fr*)nullptr, (const Fr*)nullptr, Fr::zero(), 0, (const Fr*)nullptr);
         else
-            G16_LAUNCH(ctx, k_ntt_pass<false>, (unsigned)blocks, kNttThreads, smem, st, data, tw, t->log_n, p.s_lo, p.nlev,
+            G16_LAUNCH(ctx, k_ntt_pass<false>, grid, kNttThreads, smem, st, batch, tw, t->log_n, p.s_lo, p.nlev,
                        p.t_log, first ? pre : (const Fr*)nullptr, (const Fr*)nullptr, Fr::zero(), 0, (const Fr*)nullptr);
     }
     return G16_OK;
+}
+int ntt_dif(g16_ctx* ctx, Fr* data, NttTables* t, bool inverse_root, const Fr* pre, cudaStream_t st) {
+    Fr* one[1] = {data};
+    return ntt_dif_batch(ctx, one, 1, t, inverse_root, pre, st);
 }
 
 __global__ void k_bitrev(Fr* __restrict__ data, unsigned log_n) {

@@ -222,12 +222,19 @@ int witness_map_dev(g16_ctx* ctx, int reduction, cudaStream_t st) {
         //     h = coset_iFFT((A'*B' - C') / Z) = (coset_iFFT(A'*B') - iFFT(c)) / (g^n - 1)
         // as exact field identities, whatever the witness: c needs ONE transform, and the quotient kernel disappears.
         //   a, b: iNTT (1/n deferred into the coset table) -> coset NTT, evaluations bit-reversed
-        G16_TRY(ntt_dit(ctx, a, t, true, nullptr, nullptr, st));
-        G16_TRY(ntt_dit(ctx, b, t, true, nullptr, nullptr, st));
-        G16_TRY(ntt_dif(ctx, a, t, false, t->coset_scaled, st));
-        G16_TRY(ntt_dif(ctx, b, t, false, t->coset_scaled, st));
-        //   c: coefficients / (g^n - 1), natural order
-        G16_TRY(ntt_dit(ctx, c, t, true, nullptr, &t->zinv_n, st));
+        //   c:    iNTT with 1 / (n (g^n - 1)) on the last store: coefficients / (g^n - 1), natural order
+        // the three inverse transforms run as one batched launch per pass, the two coset transforms as another (ntt.cu: NttBatch)
+        Fr* abc[3] = {a, b, c};
+        if (ctx->opt_ntt_batch) {
+            G16_TRY(ntt_dit_batch(ctx, abc, 3, t, true, nullptr, &t->zinv_n, 4u, st));
+            G16_TRY(ntt_dif_batch(ctx, abc, 2, t, false, t->coset_scaled, st));
+        } else {
+            G16_TRY(ntt_dit(ctx, a, t, true, nullptr, nullptr, st));
+            G16_TRY(ntt_dit(ctx, b, t, true, nullptr, nullptr, st));
+            G16_TRY(ntt_dif(ctx, a, t, false, t->coset_scaled, st));
+            G16_TRY(ntt_dif(ctx, b, t, false, t->coset_scaled, st));
+            G16_TRY(ntt_dit(ctx, c, t, true, nullptr, &t->zinv_n, st));
+        }
         //   coset iNTT of a*b (product taken on the first load; g^-i / (n (g^n - 1)) and the subtraction on the last store)
         G16_TRY(ntt_dit(ctx, a, t, true, t->coset_inv_z, nullptr, st, b, c));
     } else if (reduction == G16_REDUCTION_CIRCOM) {
@@ -236,12 +243,18 @@ int witness_map_dev(g16_ctx* ctx, int reduction, cudaStream_t st) {
         G16_LAUNCH(ctx, k_pad_rows, pb, 128, 0, st, ctx->d_z, a, b, (Fr*)nullptr, ctx->nc, ctx->ni, (uint64_t)n, lr);
         // c_i = a_i * b_i for i < nc; b is zero on the padding rows so the product is zero there as the reference's c
         G16_LAUNCH(ctx, k_mul_into, eb, 256, 0, st, a, b, c, n);
-        G16_TRY(ntt_dit(ctx, a, t, true, nullptr, nullptr, st));
-        G16_TRY(ntt_dit(ctx, b, t, true, nullptr, nullptr, st));
-        G16_TRY(ntt_dit(ctx, c, t, true, nullptr, nullptr, st));
-        G16_TRY(ntt_dif(ctx, a, t, false, t->odd_scaled, st));
-        G16_TRY(ntt_dif(ctx, b, t, false, t->odd_scaled, st));
-        G16_TRY(ntt_dif(ctx, c, t, false, t->odd_scaled, st));
+        Fr* abc[3] = {a, b, c};
+        if (ctx->opt_ntt_batch) {
+            G16_TRY(ntt_dit_batch(ctx, abc, 3, t, true, nullptr, nullptr, 0u, st));
+            G16_TRY(ntt_dif_batch(ctx, abc, 3, t, false, t->odd_scaled, st));
+        } else {
+            G16_TRY(ntt_dit(ctx, a, t, true, nullptr, nullptr, st));
+            G16_TRY(ntt_dit(ctx, b, t, true, nullptr, nullptr, st));
+            G16_TRY(ntt_dit(ctx, c, t, true, nullptr, nullptr, st));
+            G16_TRY(ntt_dif(ctx, a, t, false, t->odd_scaled, st));
+            G16_TRY(ntt_dif(ctx, b, t, false, t->odd_scaled, st));
+            G16_TRY(ntt_dif(ctx, c, t, false, t->odd_scaled, st));
+        }
         G16_LAUNCH(ctx, k_mul_sub, eb, 256, 0, st, a, b, c, n);
         G16_TRY(bitrev_permute(ctx, a, ctx->log_n, st));  // evaluations are the output here: natural order needed
     } else {

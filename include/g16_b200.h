@@ -201,6 +201,7 @@ int g16_get_timings(g16_ctx* ctx, g16_timings* out);
  * "wm_priority" = 1 runs the witness map and the h MSM on a high-priority stream (default 0),
  * "ntt_radix4" = 0 / 1 forces the radix-2 / radix-4 transform passes (default -1: radix-4 only when no MSM runs beside),
  * "spmv_sell" = 0 selects the row-per-thread CSR kernel instead of the sliced-ELL one (default 1),
+ * "ntt_batch" = 0 runs the witness map's transforms one launch per vector and pass instead of batched (default 1),
  * "graph" = 0 queues every launch of a proof eagerly instead of replaying the captured launch sequences as CUDA graphs
  *   (default 1; the first run of a sequence is always eager, the second is captured),
  * "asm_tables" = 0 computes the (r, s)-only points of the assembly with one lane per scalar multiplication instead of the

@@ -102,6 +102,31 @@ def test_device_montgomery_code_on_host_matches_oracle(host_fp, name, p):
     assert dec(_call(fn, 10, le(0), le(0))) == 0
 
 
+def test_windowed_scalar_mul_on_host_matches_oracle(host_fp):
+    """ec.cuh scalar_mul_window (k_scale_point: s * MSM_a, r * MSM_b1) against the oracle and the plain double-and-add: edge
+    scalars (0, 1, 8, 9, all-ones nibbles, r - 1, 2^255-ish carries into the 65th digit) and random ones."""
+    rnd = random.Random(9)
+    q = o.Q_MOD
+    enc = lambda P: b"".join(((v << 256) % q).to_bytes(32, "little") for v in P)
+    rinv = pow(1 << 256, -1, q)
+    def dec(b):
+        x, y = (int.from_bytes(b[i:i + 32], "little") * rinv % q for i in (0, 32))
+        return None if x == 0 and y == 0 else (x, y)
+    P = o.G1.mul(o.G1_GEN, 0xC0FFEE1234567)
+    ks = [0, 1, 2, 7, 8, 9, 15, 16, 0x88888888, (1 << 256) - 1, int("9" * 64, 16), int("8" * 64, 16), o.R_MOD - 1, o.R_MOD, 1 << 255]
+    ks += [rnd.randrange(1 << 256) for _ in range(12)] + [rnd.randrange(o.R_MOD) for _ in range(12)]
+    for k in ks:
+        outs = []
+        for which in (0, 1):
+            A = ctypes.create_string_buffer(enc(P), 64)
+            K = ctypes.create_string_buffer(k.to_bytes(32, "little"), 32)
+            R = ctypes.create_string_buffer(64)
+            host_fp.host_g1_scalar_mul(A, K, which, R)
+            outs.append(dec(R.raw))
+        want = o.G1.to_affine(o.G1.jmul(o.G1.to_jac(P), k))
+        assert outs[0] == want and outs[1] == want, hex(k)
+
+
 def test_device_fq2_code_on_host_matches_oracle(host_fp):
     rnd = random.Random(2)
     enc = lambda x: b"".join(((v << 256) % o.Q_MOD).to_bytes(32, "little") for v in x)
