@@ -65,7 +65,7 @@ struct MsmScratch {
     uint32_t *s_tkeys = nullptr, *s_tvals = nullptr;  // tasks sorted by length: (kTaskLen - len, task id)
     // batched-affine level tables (msm_affine.cu)
     int ba_levels = 0;
-    size_t ba_stride = 0, ba_tstride = 0;
+    size_t ba_stride = 0, ba_tstride = 0, ba_items = 0;
     uint32_t* ba_start0 = nullptr;     // first sorted position of every bucket
     uint32_t* ba_lvl = nullptr;        // [levels+1][nbuckets+1]: row 0 counts, rows 1.. offsets after each level
     uint32_t* ba_tb = nullptr;         // [levels][2][tstride]: first / last bucket of every level-kernel thread

@@ -9,7 +9,7 @@
 // products per addition once M is large.  Independent additions are what a bucket tree provides: level k adds the points
 // of every bucket pairwise (2i, 2i+1), halving each bucket, so level k of ALL buckets is one flat list of independent
 // additions.  Per level, three kernels:
-//     k_ba_products  thread t walks its kBaK consecutive output slots, multiplies the denominators x2 - x1 into a
+//     k_ba_products  thread t walks its K consecutive output slots (K per level, ba_slots_per_thread), multiplies the denominators x2 - x1 into a
 //                    running product (stored per slot: the prefix products) and emits its total T[t];
 //     k_ba_invert    one warp per 32 * kBaGroup totals: prefix products, a shuffle product tree, ONE binary-GCD inversion,
 //                    the tree walked back down, back-substitution => 1/T[t];
@@ -101,9 +101,13 @@ __global__ void k_ba_counts(const uint32_t* __restrict__ bucket_start, unsigned 
 }
 
 // first / last bucket touched by every thread of the level kernels (blockIdx.y = output level - 1)
+struct BaKs {
+    int k[kBaMaxLevels];
+};
 __global__ void k_ba_thread_buckets(const uint32_t* __restrict__ lvl, size_t stride, size_t nbuckets,
-                                    uint32_t* __restrict__ tb, size_t tstride) {
+                                    uint32_t* __restrict__ tb, size_t tstride, BaKs ks) {
     const unsigned k = blockIdx.y + 1;
+    const int kBaK = ks.k[blockIdx.y];
     const uint32_t* off = lvl + (size_t)k * stride;
     const uint32_t total = off[nbuckets];
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,7 +142,8 @@ template <class F, bool L0>
 __global__ void __launch_bounds__(128)
     k_ba_products(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ in_start,
                   const uint32_t* __restrict__ in_cnt, const uint32_t* __restrict__ out_off, size_t nbuckets,
-                  const uint32_t* __restrict__ tb_first, Fq* __restrict__ pre, Fq* __restrict__ T, Fq* __restrict__ den_out) {
+                  const uint32_t* __restrict__ tb_first, Fq* __restrict__ pre, Fq* __restrict__ T, Fq* __restrict__ den_out,
+                  const int kBaK) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = out_off[nbuckets];
     const size_t o0 = t * kBaK;
@@ -193,7 +198,7 @@ __device__ __forceinline__ Fq shfl_fq(const Fq& a, unsigned src_lane) {
     return r;
 }
 __global__ void __launch_bounds__(128)
-    k_ba_invert(const uint32_t* __restrict__ out_off, size_t nbuckets, const Fq* __restrict__ T, Fq* __restrict__ Q) {
+    k_ba_invert(const uint32_t* __restrict__ out_off, size_t nbuckets, const Fq* __restrict__ T, Fq* __restrict__ Q, const int kBaK) {
     const uint32_t total = out_off[nbuckets];
     const size_t nT = ((size_t)total + kBaK - 1) / kBaK;
     const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,10 +241,10 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-static int ba_invert(g16_ctx* ctx, const uint32_t* out_off, size_t nbuckets, size_t threads, Fq* T, Fq* Q, cudaStream_t st) {
+static int ba_invert(g16_ctx* ctx, const uint32_t* out_off, size_t nbuckets, size_t threads, Fq* T, Fq* Q, int kBaK, cudaStream_t st) {
     size_t inv_threads = (threads + kBaGroup - 1) / kBaGroup;
     inv_threads = (inv_threads + 31) / 32 * 32;
-    G16_LAUNCH(ctx, k_ba_invert, (unsigned)((inv_threads + 127) / 128), 128, 0, st, out_off, nbuckets, (const Fq*)T, Q);
+    G16_LAUNCH(ctx, k_ba_invert, (unsigned)((inv_threads + 127) / 128), 128, 0, st, out_off, nbuckets, (const Fq*)T, Q, kBaK);
     return G16_OK;
 }
 
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fq) ? G16_BA_MINB : 3
     k_ba_add(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ in_start,
              const uint32_t* __restrict__ in_cnt, const uint32_t* __restrict__ out_off, size_t nbuckets,
              const uint32_t* __restrict__ tb_last, const Fq* __restrict__ pre, const Fq* __restrict__ Tinv,
-             Affine<F>* __restrict__ out, const Fq* __restrict__ den_in) {
+             Affine<F>* __restrict__ out, const Fq* __restrict__ den_in, const int kBaK) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = out_off[nbuckets];
     const size_t o0 = t * kBaK;
@@ -378,6 +383,19 @@ __global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fq) ? G16_BA_MINB : 3
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------
+// Output slots per thread at level k (0-based): one shared-inversion chain per thread.  16 at full size (the inversion is then
+// amortised over 16 x 256 additions); fewer when the level is small -- a thread walks its slots one after the other, so on a
+// level of a few hundred thousand slots 16 per thread meant ~1 wave of blocks each running a 16-deep dependent chain (the
+// small shards of an 8-GPU run, small circuits).  Chosen from the level's capacity on the host: the launch sequence stays static.
+int ba_slots_per_thread(size_t items, size_t nbuckets, int level) {
+    const size_t cap = ba_level_cap(items, nbuckets, level + 1);
+    const size_t target_threads = (size_t)kNumSMs * 6 * 128 * 3;  // three waves of resident k_ba_add blocks
+    size_t k = (cap + target_threads - 1) / target_threads;
+    if (k < 2) k = 2;
+    if (k > (size_t)kBaKMax) k = kBaKMax;
+    return (int)k;
+}
+
 size_t ba_level_cap(size_t items, size_t nbuckets, int level) {
     size_t cap = items;
     for (int k = 0; k < level; k++) cap = (cap + nbuckets) / 2 + 1;
@@ -409,7 +427,13 @@ int ba_alloc(g16_ctx* ctx, int group, MsmScratch* sc, size_t items, size_t nbuck
     G16_TRY(dev_alloc(ctx, &sc->ba_lvl, (size_t)(levels + 1) * sc->ba_stride));
     if (levels == 0) return G16_OK;
     size_t cap1 = ba_level_cap(items, nbuckets, 1);
-    size_t threads = (cap1 + kBaK - 1) / kBaK;
+    size_t threads = 0;
+    for (int k = 0; k < levels; k++) {
+        const size_t K = (size_t)ba_slots_per_thread(items, nbuckets, k);
+        const size_t th = (ba_level_cap(items, nbuckets, k + 1) + K - 1) / K;
+        if (th > threads) threads = th;
+    }
+    sc->ba_items = items;
     sc->ba_tstride = threads + 1;
     G16_TRY(dev_alloc(ctx, &sc->ba_tb, (size_t)levels * 2 * sc->ba_tstride));
     size_t pb = group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);
@@ -436,8 +460,10 @@ int ba_build_levels(g16_ctx* ctx, MsmScratch* dg, unsigned nseg, uint32_t nb, in
     if (levels == 0) return G16_OK;
     G16_TRY(exclusive_scan_batched(ctx, dg->ba_lvl + dg->ba_stride, nbuckets + 1, dg->ba_stride, (unsigned)levels, dg->task_tmp, st));
     size_t threads = dg->ba_tstride - 1;
+    BaKs ks;
+    for (int k = 0; k < kBaMaxLevels; k++) ks.k[k] = k < levels ? ba_slots_per_thread(dg->ba_items, nbuckets, k) : kBaKMax;
     G16_LAUNCH(ctx, k_ba_thread_buckets, dim3((unsigned)((threads + 255) / 256), (unsigned)levels), 256, 0, st, dg->ba_lvl,
-               dg->ba_stride, nbuckets, dg->ba_tb, dg->ba_tstride);
+               dg->ba_stride, nbuckets, dg->ba_tb, dg->ba_tstride, ks);
     return G16_OK;
 }
 
@@ -447,6 +473,7 @@ static int ba_run_levels_t(g16_ctx* ctx, const MsmBases* mb, MsmScratch* sc, con
     const Affine<F>* src = (const Affine<F>*)mb->pts;
     for (int k = 0; k < levels; k++) {
         size_t cap = ba_level_cap(items, nbuckets, k + 1);
+        const int kBaK = ba_slots_per_thread(dg->ba_items, nbuckets, k);  // the K the thread -> bucket tables were built with
         size_t threads = (cap + kBaK - 1) / kBaK;
         unsigned grid = (unsigned)((threads + 127) / 128);
         const uint32_t* out_off = dg->ba_lvl + (size_t)(k + 1) * dg->ba_stride;
@@ -461,18 +488,18 @@ static int ba_run_levels_t(g16_ctx* ctx, const MsmBases* mb, MsmScratch* sc, con
         Fq* den = (Fq*)sc->ba_den;  // G2 only
         if (k == 0) {
             G16_LAUNCH(ctx, (k_ba_products<F, true>), grid, 128, 0, st, src, dg->s_vals, in_start, in_cnt, out_off, nbuckets, tb_first, pre, T,
-                       den);
-            G16_TRY(ba_invert(ctx, out_off, nbuckets, threads, T, Q, st));
+                       den, kBaK);
+            G16_TRY(ba_invert(ctx, out_off, nbuckets, threads, T, Q, kBaK, st));
             if (add0_ev0) G16_CUDA(ctx, cudaEventRecord(add0_ev0, st));
             G16_LAUNCH(ctx, (k_ba_add<F, true>), grid, 128, 0, st, src, dg->s_vals, in_start, in_cnt, out_off, nbuckets, tb_last,
-                           (const Fq*)pre, (const Fq*)Q, dst, (const Fq*)den);
+                           (const Fq*)pre, (const Fq*)Q, dst, (const Fq*)den, kBaK);
             if (add0_ev1) G16_CUDA(ctx, cudaEventRecord(add0_ev1, st));
         } else {
             G16_LAUNCH(ctx, (k_ba_products<F, false>), grid, 128, 0, st, src, (const uint32_t*)nullptr, in_start, in_cnt, out_off, nbuckets,
-                       tb_first, pre, T, den);
-            G16_TRY(ba_invert(ctx, out_off, nbuckets, threads, T, Q, st));
+                       tb_first, pre, T, den, kBaK);
+            G16_TRY(ba_invert(ctx, out_off, nbuckets, threads, T, Q, kBaK, st));
             G16_LAUNCH(ctx, (k_ba_add<F, false>), grid, 128, 0, st, src, (const uint32_t*)nullptr, in_start, in_cnt, out_off, nbuckets,
-                           tb_last, (const Fq*)pre, (const Fq*)Q, dst, (const Fq*)den);
+                           tb_last, (const Fq*)pre, (const Fq*)Q, dst, (const Fq*)den, kBaK);
         }
         src = dst;
     }

@@ -5,11 +5,11 @@
 namespace g16 {
 
 constexpr unsigned kTaskLen = 256;  // max points per XYZZ accumulate task
-constexpr unsigned kChunk = 16;     // buckets per reduction chunk
+constexpr unsigned kChunk = 8;      // buckets per reduction chunk (16 adds + a ~17-bit double-and-add per thread: the chain is pure latency)
 constexpr uint32_t kNegBit = 0x80000000u;
 
 // batched-affine bucket accumulation (msm_affine.cu)
-constexpr int kBaK = 16;          // output slots per thread: one shared-inversion chain per thread
+constexpr int kBaKMax = 16;       // output slots per thread at full size (one shared-inversion chain per thread); see ba_slots_per_thread
 constexpr int kBaGroup = 8;       // thread products per Fq inversion in k_ba_invert
 constexpr int kBaMaxLevels = 8;   // pairwise levels run in affine form before the XYZZ tail
 constexpr int kBaDefaultLevels = 5;
@@ -59,6 +59,7 @@ int radix_sort(g16_ctx* ctx, uint32_t** keys, uint32_t** vals, uint32_t** keys_a
 // ---- msm_affine.cu ------------------------------------------------------------------------------------------------------
 // upper bound of the number of points left after `level` pairwise levels
 size_t ba_level_cap(size_t items, size_t nbuckets, int level);
+int ba_slots_per_thread(size_t items, size_t nbuckets, int level);
 int ba_alloc(g16_ctx* ctx, int group, MsmScratch* sc, size_t items, size_t nbuckets, int levels);
 void ba_free(MsmScratch* sc);
 // level tables of a digit set: per-bucket point counts and offsets after every pairwise level (point independent)
