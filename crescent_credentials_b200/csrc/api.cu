@@ -512,6 +512,22 @@ int g16_upload_witness_async(g16_ctx* ctx, const uint64_t* z, int shard_only) {
     return G16_OK;
 }
 
+int g16_memcpy_h2d_async(void* dst_dev, const void* src_host, size_t bytes, void* stream) {
+    if (!dst_dev || !src_host) return G16_ERR_BAD_ARG;
+    return cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream) == cudaSuccess ? G16_OK : G16_ERR_CUDA;
+}
+
+int g16_upload_witness_dev(g16_ctx* ctx, const void* z_dev) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "no R1CS loaded");
+    if (!z_dev) return set_err(ctx, G16_ERR_BAD_ARG, "witness pointer is NULL");
+    G16_CUDA(ctx, cudaMemcpyAsync(ctx->d_z, z_dev, ctx->m * 32, cudaMemcpyDeviceToDevice, ctx->main));
+    ctx->witness_resident = true;
+    ctx->witness_partial = true;
+    return G16_OK;
+}
+
 int g16_r1cs_eval(g16_ctx* ctx, const uint64_t* z, uint64_t* az, uint64_t* bz, uint64_t* cz) {
     if (!ctx) return G16_ERR_BAD_ARG;
     Guard g(ctx);

@@ -461,63 +461,6 @@ struct alignas(16) Fp {
         r1 = out[1];
         r2 = out[2];
     }
-    // Two independent Montgomery products in lock-step (same scheme as mul_cios3): four carry chains in flight per thread.
-    // k_ba_add uses it for the two products that hang off the running inverse (inv_den = run * prefix, run = run * den), which
-    // are independent of each other.  Bit-identical to two mul_cios calls.
-    static G16_HD void mul_cios2(const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, Fp& r0, Fp& r1) {
-        uint32_t A[2][8], B[2][8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            A[0][k] = a0.v[k], A[1][k] = a1.v[k];
-            B[0][k] = b0.v[k], B[1][k] = b1.v[k];
-        }
-        uint32_t X[2][8], Y[2][8];
-        uint32_t m[2], cy[2];
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            lanes_mul(X[j], A[j][0], A[j][2], A[j][4], A[j][6], B[j][0]);
-            lanes_mul(Y[j], A[j][1], A[j][3], A[j][5], A[j][7], B[j][0]);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            m[j] = X[j][0] * PR::INV;
-            lanes_mad(Y[j], PR::P(1), PR::P(3), PR::P(5), PR::P(7), m[j]);
-            cy[j] = lanes_mad(X[j], PR::P(0), PR::P(2), PR::P(4), PR::P(6), m[j]);
-            Y[j][7] += cy[j];
-        }
-#pragma unroll
-        for (int i = 1; i < 8; i++) {
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                uint32_t* ev = (i & 1) ? Y[j] : X[j];
-                uint32_t* od = (i & 1) ? X[j] : Y[j];
-                lanes_fold_shift_mad(ev[0], od, A[j][1], A[j][3], A[j][5], A[j][7], B[j][i]);
-                cy[j] = lanes_mad(ev, A[j][0], A[j][2], A[j][4], A[j][6], B[j][i]);
-                od[7] += cy[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                uint32_t* ev = (i & 1) ? Y[j] : X[j];
-                uint32_t* od = (i & 1) ? X[j] : Y[j];
-                m[j] = ev[0] * PR::INV;
-                lanes_mad(od, PR::P(1), PR::P(3), PR::P(5), PR::P(7), m[j]);
-                cy[j] = lanes_mad(ev, PR::P(0), PR::P(2), PR::P(4), PR::P(6), m[j]);
-                od[7] += cy[j];
-            }
-        }
-        Fp out[2];
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            uint32_t sh[8];
-#pragma unroll
-            for (int k = 0; k < 7; k++) sh[k] = Y[j][k + 1];
-            sh[7] = 0;
-            uint32_t c = add8(out[j].v, sh, X[j]);
-            reduce_once(out[j].v, c);
-        }
-        r0 = out[0];
-        r1 = out[1];
-    }
     // Montgomery reduction of a 16-limb value P < p * 2^256:  P * 2^-256 mod p, fully reduced.
     // Same two-accumulator scheme as mul_cios with the product rows removed: the high limbs of P enter one per round
     // at the top of the accumulator.

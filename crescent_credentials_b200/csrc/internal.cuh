@@ -179,7 +179,8 @@ struct g16_ctx {
     int opt_ba_levels = -1;  // batched-affine levels (-1 = default)
     int opt_share_digits = 1;
     int opt_spmv_sell = 1;     // sliced-ELL SpMV (0: row-per-thread CSR kernel)
-    int opt_ntt_batch = 1;     // witness map: a, b, c inverse transforms (and the a, b coset transforms) as one launch per pass
+    int opt_ntt_batch = -1;    // witness map: a, b, c inverse transforms (and the a, b coset transforms) as one launch per pass;
+                               // -1 = auto: only when nothing runs beside the transforms (like opt_ntt_radix4), 0 / 1 force
     int opt_ntt_radix4 = -1;   // k_ntt_pass4 (two butterfly levels per shared-memory round trip).  Alone it is faster (witness map
                                // 3.32 vs 3.67 ms) but beside the MSM chains it costs +1.1 ms per proof (profiles/r01_sched_sweep_*):
                                // -1 = auto: radix-4 when nothing runs beside the transforms (stand-alone calls, serialize, a

@@ -261,14 +261,8 @@ __device__ __forceinline__ void ba_add_pair(Affine<F>& p1, const Affine<F>& p2, 
     }
     Fq den = sizeof(F) == sizeof(Fq) ? BaField<F>::den(d) : ld_vec(den_in + o);  // G2: the norm k_ba_products stored
     Fq inv_den;
-#ifdef G16_BA_MUL2
-    // the two products that hang off the running inverse are independent: row-interleaved (four carry chains)
-    (void)first;
-    Fq::mul_cios2(run, prefix, run, den, inv_den, run);
-#else
     inv_den = first ? run : run * prefix;
     run = run * den;
-#endif
     F inv_d = BaField<F>::inv(d, inv_den);
     F num;
     if (kind == BA_ADD) {
@@ -283,11 +277,8 @@ __device__ __forceinline__ void ba_add_pair(Affine<F>& p1, const Affine<F>& p2, 
     p1.x = x3;
 }
 
-#ifndef G16_BA_MINB
-#define G16_BA_MINB 6  // resident blocks per SM the G1 build is held to (80 registers; a few bytes of spill in the restructured loop)
-#endif
 template <class F, bool L0>
-__global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fq) ? G16_BA_MINB : 3)
+__global__ void __launch_bounds__(128)
     k_ba_add(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ in_start,
              const uint32_t* __restrict__ in_cnt, const uint32_t* __restrict__ out_off, size_t nbuckets,
              const uint32_t* __restrict__ tb_last, const Fq* __restrict__ pre, const Fq* __restrict__ Tinv,
@@ -302,15 +293,11 @@ __global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fq) ? G16_BA_MINB : 3
     uint32_t s_base = in_start[g];
     uint32_t s_cnt = in_cnt ? in_cnt[g] : in_start[g + 1] - s_base;
     Fq run = ld_vec(Tinv + t);
-    // ncu (profiles/r02_ncu_ba_add_h.txt): 44 % of this kernel's stall samples were long_scoreboard, spread over FIVE exposed
-    // latencies per slot -- reference 1, point 1, reference 2, point 2, prefix -- because each load was consumed (sign applied)
-    // before the next one was issued.  Here a slot's data loads are issued back to back, the sign flips come afterwards, and
-    // the position + references of the NEXT slot are fetched while the gathers of this one are in flight (G16_BA_V = 0 keeps
-    // the round-1 loop for the A/B record).
-#ifndef G16_BA_V
-#define G16_BA_V 1
-#endif
-#if G16_BA_V == 0
+    // Measured and not adopted (profiles/r02_ab_ba_add_ntt_batch.log, h-query level 0 timed alone / whole proof): issuing a
+    // slot's loads back to back with the next slot's references prefetched under the gathers -- 1.548 ms / 33.7 ms at 80
+    // registers with spills, 1.482 / 33.3 at 96 registers and 5 blocks per SM, against 1.462 / 33.8 for this loop; the two
+    // products off the running inverse row-interleaved (four carry chains) -- 1.574 / 34.3.  Level 0 is bound by the random
+    // 128-byte DRAM granules of its gathers (379 B of DRAM traffic per slot, ncu), not by exposed latency or by ILP.
 #pragma unroll 1
     for (uint32_t o = o_last;; o--) {
         while (o < g_off) {
@@ -330,56 +317,6 @@ __global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fq) ? G16_BA_MINB : 3
         st_vec(out + o, p1);
         if (o == (uint32_t)o0) break;
     }
-#else
-    auto locate = [&](uint32_t oo, uint32_t& s, bool& pair) {  // called with descending oo
-        while (oo < g_off) {
-            g--;
-            g_off = out_off[g];
-            s_base = in_start[g];
-            s_cnt = in_cnt ? in_cnt[g] : in_start[g + 1] - s_base;
-        }
-        const uint32_t i = oo - g_off;
-        s = s_base + 2 * i;
-        pair = 2 * i + 1 < s_cnt;
-    };
-    uint32_t s, r1 = 0, r2 = 0;
-    bool pair;
-    locate(o_last, s, pair);
-    if (L0) {
-        r1 = vals[s];
-        if (pair) r2 = vals[s + 1];
-    }
-    uint32_t o = o_last;
-#pragma unroll 1
-    for (;;) {
-        // this slot's operands: all loads in flight together
-        Affine<F> p1 = L0 ? ldg_vec(src + (r1 & ~kNegBit)) : ld_vec(src + s);
-        Affine<F> p2 = p1;
-        Fq prefix = Fq::one();
-        const bool first = o == (uint32_t)o0;
-        if (pair) {
-            p2 = L0 ? ldg_vec(src + (r2 & ~kNegBit)) : ld_vec(src + s + 1);
-            if (!first) prefix = ld_vec(pre + o - 1);
-        }
-        const uint32_t c1 = r1, c2 = r2, co = o;
-        const bool cpair = pair;
-        if (!first) {  // next slot: bucket walk and references while the gathers travel
-            locate(o - 1, s, pair);
-            if (L0) {
-                r1 = vals[s];
-                if (pair) r2 = vals[s + 1];
-            }
-        }
-        if (L0 && (c1 & kNegBit)) p1.y = p1.y.neg();
-        if (cpair) {
-            if (L0 && (c2 & kNegBit)) p2.y = p2.y.neg();
-            ba_add_pair<F>(p1, p2, prefix, first, run, den_in, co);
-        }
-        st_vec(out + co, p1);
-        if (first) break;
-        o = co - 1;
-    }
-#endif
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------

@@ -223,9 +223,13 @@ int witness_map_dev(g16_ctx* ctx, int reduction, cudaStream_t st) {
         // as exact field identities, whatever the witness: c needs ONE transform, and the quotient kernel disappears.
         //   a, b: iNTT (1/n deferred into the coset table) -> coset NTT, evaluations bit-reversed
         //   c:    iNTT with 1 / (n (g^n - 1)) on the last store: coefficients / (g^n - 1), natural order
-        // the three inverse transforms run as one batched launch per pass, the two coset transforms as another (ntt.cu: NttBatch)
+        // a lone witness map (a shard rank without wire MSMs, serialised runs) batches the three inverse transforms into one
+        // launch per pass and the two coset transforms into another (ntt.cu: NttBatch; 3.29 -> 3.21 ms).  Beside the MSM chains
+        // the batched launches were measured to cost the whole proof +4 ms (33.7 vs 29.9 ms, profiles/
+        // r02_ab_ba_add_ntt_batch.log): 3072-block launches of 64 KB-shared-memory blocks crowd the DRAM-bound MSM kernels out
+        // of the SMs, so there the transforms stay one modest launch each.
         Fr* abc[3] = {a, b, c};
-        if (ctx->opt_ntt_batch) {
+        if (ctx->opt_ntt_batch > 0 || (ctx->opt_ntt_batch < 0 && ctx->wm_alone)) {
             G16_TRY(ntt_dit_batch(ctx, abc, 3, t, true, nullptr, &t->zinv_n, 4u, st));
             G16_TRY(ntt_dif_batch(ctx, abc, 2, t, false, t->coset_scaled, st));
         } else {
@@ -244,7 +248,7 @@ int witness_map_dev(g16_ctx* ctx, int reduction, cudaStream_t st) {
         // c_i = a_i * b_i for i < nc; b is zero on the padding rows so the product is zero there as the reference's c
         G16_LAUNCH(ctx, k_mul_into, eb, 256, 0, st, a, b, c, n);
         Fr* abc[3] = {a, b, c};
-        if (ctx->opt_ntt_batch) {
+        if (ctx->opt_ntt_batch > 0 || (ctx->opt_ntt_batch < 0 && ctx->wm_alone)) {
             G16_TRY(ntt_dit_batch(ctx, abc, 3, t, true, nullptr, nullptr, 0u, st));
             G16_TRY(ntt_dif_batch(ctx, abc, 3, t, false, t->odd_scaled, st));
         } else {

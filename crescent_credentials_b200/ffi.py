@@ -30,7 +30,7 @@ EXPORTS = [
     "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count", "g16_set_option",
     "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare", "g16_get_msm_stats", "g16_ctx_load_pk_ranges",
     "g16_prove_shard_begin_dev", "g16_prove_shard_finish_dev", "g16_copy_h_dev",
-    "g16_upload_witness_async", "g16_msm_copy_result_dev", "g16_msm_combine_dev", "g16_graph_stats",
+    "g16_upload_witness_async", "g16_upload_witness_dev", "g16_memcpy_h2d_async", "g16_msm_copy_result_dev", "g16_msm_combine_dev", "g16_graph_stats",
     "g16_ctx_load_vk", "g16_vk_alpha_beta", "g16_prepare_inputs", "g16_verify_batch", "g16_verify_batch_prepared",
     "g16_verify_batch_dev", "g16_pairing", "g16_host_alloc", "g16_host_free",
 ]
@@ -126,6 +126,8 @@ def load_library() -> C.CDLL:
     lib.g16_prove.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ProofOut)]
     lib.g16_upload_witness.argtypes = [C.c_void_p, C.c_void_p]
     lib.g16_upload_witness_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.g16_upload_witness_dev.argtypes = [C.c_void_p, C.c_void_p]
+    lib.g16_memcpy_h2d_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.g16_prove_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ProofOut)]
     lib.g16_prove_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Partial)]
     lib.g16_prove_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
@@ -171,6 +173,15 @@ def load_library() -> C.CDLL:
     lib.g16_pairing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     _lib = lib
     return lib
+
+
+def memcpy_h2d_async(dst_dev: int, src_host: int, nbytes: int, stream: int):
+    """cudaMemcpyAsync(host -> device) on a raw stream handle, through the runtime the library is linked with (used by the
+    sharded host glue for page-locked witness chunks that are addressed by pointer, not by a torch tensor)."""
+    lib = load_library()
+    rc = lib.g16_memcpy_h2d_async(C.c_void_p(dst_dev), C.c_void_p(src_host), C.c_size_t(nbytes), C.c_void_p(stream))
+    if rc != G16_OK:
+        raise G16Error(rc, "cudaMemcpyAsync(host -> device) failed")
 
 
 def _ptr(a):
@@ -434,6 +445,10 @@ class Context:
             z = np.ascontiguousarray(z, dtype=np.uint64)
             self._check_z(z)
         self.check(self.lib.g16_upload_witness_async(self.h, _ptr(z), int(shard_only)))
+
+    def upload_witness_dev(self, z_dev: int):
+        """The whole witness from device memory (stream-ordered device-to-device copy)."""
+        self.check(self.lib.g16_upload_witness_dev(self.h, C.c_void_p(z_dev)))
 
     def prove_resident(self, r, s, reduction=REDUCTION_LIBSNARK) -> ProofOut:
         r = np.ascontiguousarray(r, dtype=np.uint64)

@@ -97,7 +97,8 @@ class ShardedProver:
     combine is a single stream-ordered chain, with no host synchronisation before the proof read-back on rank 0."""
 
     def __init__(self, pk: ProvingKey, matrices: ConstraintMatrices, device: int, rank: int, world: int, stream=None,
-                 precompute: bool = False, plan: Optional[ShardPlan] = None, ctx: Optional[ffi.Context] = None):
+                 precompute: bool = False, plan: Optional[ShardPlan] = None, ctx: Optional[ffi.Context] = None,
+                 gather_upload: bool = True):
         """stream: a torch.cuda.Stream (default: a new one on `device`).  ctx: an existing context that was created on that
         stream's handle (its R1CS / key are loaded here); default: a new context."""
         import torch
@@ -131,6 +132,14 @@ class ShardedProver:
                 if rank == self.plan.wm_rank:
                     self.h_all = torch.zeros((cap, 4), dtype=torch.int64, device=dev)
                 self.h_mine = torch.zeros((self.plan.h_chunk, 4), dtype=torch.int64, device=dev)
+            # gathered upload (staggered plan): every rank's 1/G chunk of z, and the assembled vector on the witness-map rank
+            self.gather_upload = bool(gather_upload) and world > 1 and self.plan.staggered
+            self.z_chunk_len = -(-m // world)
+            self.z_chunk = self.z_all = None
+            if self.gather_upload:
+                self.z_chunk = torch.zeros((self.z_chunk_len, 4), dtype=torch.int64, device=dev)
+                if rank == self.plan.wm_rank:
+                    self.z_all = torch.zeros((world * self.z_chunk_len, 4), dtype=torch.int64, device=dev)
         self.stream.synchronize()
         self.z_pin = None          # page-locked staging of the witness for prove()
         self._z_done = None        # event: the last upload from z_pin has been consumed
@@ -140,9 +149,13 @@ class ShardedProver:
         return (not self.plan.staggered) or self.rank == self.plan.wm_rank
 
     def upload_witness(self, z_host):
-        """Stream-ordered upload of this rank's part of the witness: the whole of z on a rank that runs the witness map,
-        only the slice its wire MSMs read elsewhere.  z_host: a page-locked host ADDRESS (int) of m x 4 u64 words that stays
-        valid until the proof is done, or a numpy array (then staged through an internal page-locked buffer)."""
+        """Stream-ordered upload of the witness (the same z on every rank).  z_host: a page-locked host ADDRESS (int) of m x 4
+        u64 words that stays valid until the proof is done, or a numpy array (staged through an internal page-locked buffer).
+
+        Staggered plan: a rank that does not run the witness map uploads only the slice of z its wire MSMs read.  The rank that
+        does run it needs all of z -- 32 m bytes over ONE PCIe link would sit at the head of its critical path (46 MB: 0.8 ms
+        for S-rs256) -- so every rank uploads 1/G of z over its own link and one NCCL gather over NVLink assembles the vector on
+        that rank (`gather_upload`, default on for G > 1).  Uniform plan: every rank runs the witness map and uploads all of z."""
         torch = self.torch
         if isinstance(z_host, np.ndarray):
             z = np.ascontiguousarray(z_host, dtype=np.uint64).reshape(-1, 4)
@@ -154,11 +167,30 @@ class ShardedProver:
             else:
                 self._z_done.synchronize()   # the previous proof's copy must have left the staging buffer
             self.z_pin.numpy()[:] = z.view(np.int64)
-            self.ctx.upload_witness_async(self.z_pin.data_ptr(), shard_only=not self.runs_witness_map)
+            addr = self.z_pin.data_ptr()
+        else:
+            addr = int(z_host)
+        if not self.plan.staggered:
+            self.ctx.upload_witness_async(addr, shard_only=False)
+        elif self.gather_upload:
+            import torch.distributed as dist
+            c = self.z_chunk_len
+            lo = min(self.rank * c, self.m)
+            cnt = min(c, self.m - lo)
+            with torch.cuda.stream(self.stream):
+                if cnt:   # my 1/G of z over my own PCIe link (a raw pinned address: copy through the runtime on this stream)
+                    ffi.memcpy_h2d_async(self.z_chunk.data_ptr(), addr + lo * 32, cnt * 32, self.stream.cuda_stream)
+                owner = self.rank == self.plan.wm_rank
+                dist.gather(self.z_chunk.view(-1), list(self.z_all.view(self.world, -1)) if owner else None, dst=self.plan.wm_rank)
+                if owner:
+                    self.ctx.upload_witness_dev(self.z_all.data_ptr())
+            if not self.runs_witness_map:
+                self.ctx.upload_witness_async(addr, shard_only=True)
+        else:
+            self.ctx.upload_witness_async(addr, shard_only=not self.runs_witness_map)
+        if isinstance(z_host, np.ndarray):
             with torch.cuda.stream(self.stream):
                 self._z_done.record()
-        else:
-            self.ctx.upload_witness_async(int(z_host), shard_only=not self.runs_witness_map)
 
     def prove_resident(self, rr, ss, reduction=ffi.REDUCTION_LIBSNARK):
         """Witness already uploaded (upload_witness); (rr, ss) Montgomery.  Returns the raw proof on rank 0, None elsewhere."""

@@ -163,6 +163,13 @@ int g16_prove_resident(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], i
  * a / b_g1 / b_g2 / l ranges): enough for every rank that does not run the witness map itself (g16_prove_shard_begin_dev with
  * run_witness_map = 0), which must not pay for the other 32 * m * (1 - 1/G) bytes. */
 int g16_upload_witness_async(g16_ctx* ctx, const uint64_t* z, int shard_only);
+/* The whole witness from DEVICE memory (m Montgomery elements; stream-ordered copy on the context's main stream): lets the
+ * host glue of a sharded run bring z to the witness-map rank over several PCIe links + NVLink (every rank uploads 1/G of it,
+ * one gather) instead of over that rank's own link alone. */
+int g16_upload_witness_dev(g16_ctx* ctx, const void* z_dev);
+/* cudaMemcpyAsync(host -> device) on a raw cudaStream_t (the current device of the calling thread): for host glue that
+ * addresses page-locked memory by pointer. */
+int g16_memcpy_h2d_async(void* dst_dev, const void* src_host, size_t bytes, void* stream);
 
 /* MSM-sharded proving: every rank calls g16_prove_shard on its context (loaded with its shard) with the same (r, s), the
  * G partials are gathered (one small NCCL gather by the host glue) and rank 0 calls g16_prove_combine. */
@@ -201,7 +208,8 @@ int g16_get_timings(g16_ctx* ctx, g16_timings* out);
  * "wm_priority" = 1 runs the witness map and the h MSM on a high-priority stream (default 0),
  * "ntt_radix4" = 0 / 1 forces the radix-2 / radix-4 transform passes (default -1: radix-4 only when no MSM runs beside),
  * "spmv_sell" = 0 selects the row-per-thread CSR kernel instead of the sliced-ELL one (default 1),
- * "ntt_batch" = 0 runs the witness map's transforms one launch per vector and pass instead of batched (default 1),
+ * "ntt_batch" = 0 / 1 forces one launch per transform and pass / batched launches for the witness map (default -1: batched
+ *   only when no MSM runs beside the transforms),
  * "graph" = 0 queues every launch of a proof eagerly instead of replaying the captured launch sequences as CUDA graphs
  *   (default 1; the first run of a sequence is always eager, the second is captured),
  * "asm_tables" = 0 computes the (r, s)-only points of the assembly with one lane per scalar multiplication instead of the

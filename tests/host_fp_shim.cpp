@@ -19,7 +19,6 @@ template <class F> static void bin(int op, const uint32_t* a, const uint32_t* b,
         case 8: z = F::mul_karatsuba(x, y); break;
         case 9: z = x.inverse_bgcd(); break;
         case 10: z = x.inverse_safegcd(); break;
-        case 11: { F w; F::mul_cios2(x, y, y, x + y, z, w); z = z + w; break; }  // x*y + y*(x+y), both products in lock-step
         default: z = F::zero();
     }
     memcpy(r, z.v, 32);

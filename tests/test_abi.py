@@ -92,9 +92,6 @@ def test_device_montgomery_code_on_host_matches_oracle(host_fp, name, p):
     for a in vals[1:400]:
         assert dec(_call(fn, 9, le((a << 256) % p), le(0))) == (pow(a, -1, p) << 256) % p
     assert dec(_call(fn, 9, le(0), le(0))) == 0
-    # two products in lock-step (mul_cios2, k_ba_add under -DG16_BA_MUL2): same bits as two separate products
-    for a, b in zip(vals[:300], reversed(vals[:300])):
-        assert dec(_call(fn, 11, le(a), le(b))) == (a * b + b * ((a + b) % p)) * rinv % p
     # divsteps ("safegcd") inverse -- what k_ba_invert and the normalisations call: edge values, small values, 0 -> 0
     small = [rnd.randrange(1, 1 << k) for k in range(1, 254, 3)]
     for a in vals[1:1200] + small:

@@ -136,3 +136,31 @@ def test_sharded_prover_class_over_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "SHARDED_WORKER_OK" in out.stdout
+
+
+def test_witness_from_device_memory():
+    """g16_upload_witness_dev (the landing step of the gathered upload of the sharded path): the witness copied from another
+    device buffer gives the golden proof through the resident entry point."""
+    meta, r1cs_bytes, pk_bytes = load_golden("rand300")
+    mats = load_matrices(r1cs_bytes)
+    pk = g.ProvingKey.deserialize_uncompressed_unchecked(pk_bytes)
+    wires = mats.num_instance_variables + mats.num_witness_variables
+    z = g.fr_to_mont([int(v, 16) for v in meta["z"]])
+    r, s = g.fr_to_mont([int(meta["r"], 16)])[0], g.fr_to_mont([int(meta["s"], 16)])[0]
+    ctx = ffi.Context(0)
+    try:
+        ctx.load_r1cs(mats.num_constraints, mats.num_instance_variables, wires, mats.row_ptr, mats.col, mats.val, mats.encoding)
+        ctx.load_pk(pk.arrays, pk.encoding, 0, 1)
+        d = ctx.dev_alloc(z.nbytes)
+        ctx.dev_upload(d, z)
+        ctx.upload_witness_dev(d)
+        for _ in range(3):   # eager, captured, replayed
+            proof = g.Proof.from_ffi(ctx.prove_resident(r, s))
+            assert proof.serialize_uncompressed().hex() == meta["proof_uncompressed"]
+        st = ctx.graph_stats()
+        assert st["fallbacks"] == 0 and st["captures"] >= 1 and st["replays"] >= 2
+        ctx.set_option("graph", 0)   # eager launches: same bytes
+        assert g.Proof.from_ffi(ctx.prove_resident(r, s)).serialize_uncompressed().hex() == meta["proof_uncompressed"]
+        ctx.dev_free(d)
+    finally:
+        ctx.close()
