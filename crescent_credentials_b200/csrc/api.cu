@@ -939,7 +939,12 @@ static int shard_begin(g16_ctx* ctx, int reduction, bool run_wm, bool allow_hi =
 
 static int shard_finish(g16_ctx* ctx, const Fr* h_src) {
     cudaStream_t main = ctx->main;
-    cudaStream_t hs = (!h_src && ctx->sh_wm_stream) ? ctx->sh_wm_stream : main;
+    // wm_priority = 1: the h MSM stays on the witness map's (high-priority) stream; = 2: only the witness map ran there
+    cudaStream_t hs = (!h_src && ctx->sh_wm_stream && ctx->opt_wm_priority != 2) ? ctx->sh_wm_stream : main;
+    if (hs == main && ctx->sh_wm_stream && ctx->sh_wm_stream != main) {
+        G16_CUDA(ctx, cudaEventRecord(ctx->ev_hi, ctx->sh_wm_stream));
+        G16_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_hi, 0));
+    }
     PartialLayout* part = (PartialLayout*)ctx->d_partial;
     // the h MSM over h[lo..hi)  (prover.rs:63-66; the zip drops h[n-1], generator.rs:178)
     G16_TRY(run_graphed(ctx, GR_H, 0x200 ^ (uint64_t)(uintptr_t)h_src, hs, [&] {

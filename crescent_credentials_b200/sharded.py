@@ -22,9 +22,10 @@ import numpy as np
 from . import ffi
 from .groth16 import Proof, ProvingKey, ConstraintMatrices, fr_to_mont, R_MOD
 
-# witness-map time over the time of the four z-only MSMs on one B200 (S-rs256: 4.25 ms vs ~15 ms); only the balance of the
-# staggered plan depends on it, never a result
-WM_OVER_Z = 0.28
+# witness-map time over the time of the four z-only MSMs on one B200; only the balance of the staggered plan depends on it,
+# never a result.  0.28 in round 1 (4.25 ms vs ~15 ms); at N = 2 that left rank 0 done at 14.4 ms and rank 1 at 16.2 ms
+# (profiles/r02_bench_n2.json), i.e. rank 0 should take 0.40 of the wire MSMs instead of 0.36: 0.20.
+WM_OVER_Z = 0.20
 
 
 def shard_range(total: int, rank: int, world: int):
