@@ -218,7 +218,8 @@ class Runner:
         else:
             h_len = int(np.asarray(pk.arrays["h_query"]).reshape(-1, 8).shape[0])
             m1 = int(np.asarray(pk.arrays["a_query"]).reshape(-1, 8).shape[0]) - 1
-            self.plan = (sharded.staggered_plan(h_len, m1, world, args.rank0_share) if args.plan == "staggered"
+            self.plan = (sharded.staggered_plan(h_len, m1, world, args.rank0_share, None if args.wm_split < 0 else bool(args.wm_split))
+                         if args.plan == "staggered"
                          else sharded.uniform_plan(h_len, m1, world))
             self.prover = sharded.ShardedProver(pk, inst.matrices, local_rank, rank, world, stream=tstream,
                                                 precompute=bool(args.precompute), plan=self.plan, ctx=ctx)
@@ -247,7 +248,7 @@ class Runner:
         m1 = inst.m - 1
         return {"workload": f"{inst.name} ({args.witness} witness)", "constraints": inst.nc, "wires": inst.m, "domain": inst.n,
                 "nnz": nnz, "parallelism": f"msm-shard{self.world}" if self.world > 1 else "single",
-                "plan": ({"kind": args.plan, "witness_map_rank": plan.wm_rank, "rank0_wire_share": round(plan.z_ranges[0][1] / max(m1, 1), 4),
+                "plan": ({"kind": args.plan, "witness_map_rank": plan.wm_rank, "witness_map_bc_rank": plan.wm2_rank, "rank0_wire_share": round(plan.z_ranges[0][1] / max(m1, 1), 4),
                           "h_scatter_bytes_per_peer": plan.h_chunk * 32 if plan.staggered else 0} if self.world > 1 else None),
                 "l2": "inputs>L2 (pk+scratch ~GBs)", "precompute": args.precompute,
                 "window_bits": args.window_bits or "auto (19 at this size)", "ba_levels": args.ba_levels, "synthetic": SYNTH_NOTE}
@@ -294,6 +295,8 @@ def main():
     ap.add_argument("--plan", choices=["staggered", "uniform"], default="staggered",
                     help="N > 1: staggered = only rank 0 runs the witness map, the other ranks take a larger share of the wire "
                          "MSMs and receive their h chunk through one NCCL scatter; uniform = every rank runs the witness map")
+    ap.add_argument("--wm-split", type=int, default=-1, help="staggered plan: 1 / 0 force the split of the witness map over ranks 0 and "
+                    "1 on / off (default -1: on from 6 ranks)")
     ap.add_argument("--rank0-share", type=float, default=None,
                     help="staggered plan: rank 0's share of the wire MSMs (default: the balance point of sharded.rank0_wire_share)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

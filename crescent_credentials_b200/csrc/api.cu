@@ -728,7 +728,7 @@ struct PartialLayout {
 // (VERDICT r01 item 4).  Segments: FULL = a whole single-GPU proof; in the sharded path, where NCCL calls of the host glue sit
 // between the pieces, WIRE (the z-only MSM chains, on their own root stream), WM (witness map) and H (the h MSM).
 // Timing events inside a captured sequence are recorded as external event nodes, so the stage timings keep working.
-enum { GR_FULL = 0, GR_WIRE = 1, GR_WM = 2, GR_H = 3 };
+enum { GR_FULL = 0, GR_WIRE = 1, GR_WM = 2, GR_H = 3, GR_PART = 4 /* .. 7: witness-map parts A, B, C, FINAL */ };
 
 static int rec_t(g16_ctx* ctx, cudaEvent_t ev, cudaStream_t st) {
     if (ctx->capturing) G16_CUDA(ctx, cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal));
@@ -1102,6 +1102,41 @@ int g16_prove_shard_finish_dev(g16_ctx* ctx, const void* h_dev, size_t h_first, 
     G16_TRY(shard_finish(ctx, h_dev ? (const Fr*)h_dev - h_first : nullptr));
     G16_CUDA(ctx, cudaEventRecord(ctx->ev_t[12], ctx->main));
     ctx->tm_stale = true;
+    return G16_OK;
+}
+
+int g16_witness_map_part_dev(g16_ctx* ctx, int parts) {
+    if (!ctx) return G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "witness_map_part: no R1CS loaded");
+    if (!ctx->witness_resident) return set_err(ctx, G16_ERR_BAD_ARG, "witness_map_part: the whole witness must be on the device");
+    if (parts <= 0 || parts > 15) return set_err(ctx, G16_ERR_BAD_ARG, "witness_map_part: parts mask %d", parts);
+    for (int k = 0; k < 4; k++) {
+        const int bit = 1 << k;
+        if (!(parts & bit)) continue;
+        const bool alone = ctx->wm_alone;
+        G16_TRY(run_graphed(ctx, GR_PART + k, 0x400 + (uint64_t)bit, ctx->main, [&] {
+            if (bit == G16_WM_PART_A) G16_TRY(rec_t(ctx, ctx->ev_t[0], ctx->main));
+            ctx->wm_alone = true;  // a rank that runs witness-map parts has no wire MSMs beside them (sharded.py)
+            int rc = witness_map_part_dev(ctx, bit, ctx->main);
+            ctx->wm_alone = alone;
+            G16_TRY(rc);
+            if (bit == G16_WM_PART_FINAL) G16_TRY(rec_t(ctx, ctx->ev_t[1], ctx->main));
+            return G16_OK;
+        }));
+    }
+    return G16_OK;
+}
+
+int g16_wm_vector_copy_dev(g16_ctx* ctx, int which, void* ext_dev, size_t capacity_elems, int to_ctx) {
+    if (!ctx || !ext_dev || which < 0 || which > 2) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "wm_vector_copy: bad argument") : G16_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "wm_vector_copy: no R1CS loaded");
+    const size_t n = (size_t)1 << ctx->log_n;
+    if (capacity_elems < n) return set_err(ctx, G16_ERR_BAD_ARG, "wm_vector_copy: buffer holds %zu < %zu elements", capacity_elems, n);
+    Fr* v = which == 0 ? ctx->d_a : which == 1 ? ctx->d_b : ctx->d_c;
+    if (to_ctx) G16_CUDA(ctx, cudaMemcpyAsync(v, ext_dev, n * 32, cudaMemcpyDeviceToDevice, ctx->main));
+    else G16_CUDA(ctx, cudaMemcpyAsync(ext_dev, v, n * 32, cudaMemcpyDeviceToDevice, ctx->main));
     return G16_OK;
 }
 

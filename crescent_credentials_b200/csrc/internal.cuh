@@ -132,7 +132,7 @@ struct g16_ctx {
     cudaEvent_t ev_fork = nullptr;
     cudaStream_t wire = nullptr;  // root of the z-only MSM chains (forked from main, joined back at the end of a shard run)
     cudaEvent_t ev_wfork = nullptr, ev_wire_done = nullptr, ev_pre = nullptr;
-    g16::GraphSlot graphs[4];     // FULL / WIRE / WM / H launch sequences
+    g16::GraphSlot graphs[8];     // FULL / WIRE / WM / H launch sequences, WM parts A / B / C / FINAL
     uint64_t graph_epoch = 1;     // bumped by everything that changes a sequence (options, key, R1CS)
     bool capturing = false;
     uint64_t graph_replays = 0, graph_captures = 0, graph_fallbacks = 0;
@@ -265,6 +265,7 @@ int ntt_api(g16_ctx* ctx, Fr* data_dev, unsigned log_n, int inverse, int coset, 
 
 // witness.cu ------------------------------------------------------------------------------------------------------------
 int witness_map_dev(g16_ctx* ctx, int reduction, cudaStream_t st);  // z in ctx->d_z; h left in ctx->d_a (natural order)
+int witness_map_part_dev(g16_ctx* ctx, int parts, cudaStream_t st);  // LibsnarkReduction in parts (G16_WM_PART_*)
 int r1cs_eval_dev(g16_ctx* ctx, Fr* az, Fr* bz, Fr* cz, bool bitrev, cudaStream_t st);
 // builds the sliced-ELL copy of matrix k from its CSR arrays (host row_ptr for the row order, device col / val for the entries)
 int sell_build(g16_ctx* ctx, int k, const uint64_t* row_ptr_host, cudaStream_t st);

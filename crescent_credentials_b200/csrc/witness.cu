@@ -52,7 +52,7 @@ __global__ void k_pad_rows(const Fr* __restrict__ z, Fr* __restrict__ a, Fr* __r
     uint64_t p = nc + i;
     if (p >= n) return;
     uint64_t o = log_n_rev ? (uint64_t)(__brev((unsigned)p) >> (32 - log_n_rev)) : p;
-    st_fr(a + o, i < ni ? ld_fr(z + i) : Fr::zero());
+    if (a) st_fr(a + o, i < ni ? ld_fr(z + i) : Fr::zero());
     if (b) st_fr(b + o, Fr::zero());
     if (c) st_fr(c + o, Fr::zero());
 }
@@ -201,6 +201,43 @@ int r1cs_eval_dev(g16_ctx* ctx, Fr* az, Fr* bz, Fr* cz, bool bitrev, cudaStream_
     if (az) G16_TRY(spmv(ctx, 0, az, lr, st));
     if (bz) G16_TRY(spmv(ctx, 1, bz, lr, st));
     if (cz) G16_TRY(spmv(ctx, 2, cz, lr, st));
+    return G16_OK;
+}
+
+// The LibsnarkReduction witness map cut into its three independent pipelines and the final transform, so that the host glue of
+// a sharded run can place them on different GPUs (sharded.py, plan "wm_split"): parts is a mask of
+//   G16_WM_PART_A      a <- coset_NTT(iNTT(A z ++ inputs))          (r1cs_to_qap.rs:164-185, a side)
+//   G16_WM_PART_B      b <- coset_NTT(iNTT(B z))                    (:164-185, b side)
+//   G16_WM_PART_C      c <- iNTT(C z) / (g^n - 1)                   (:191-199 with the constant-Z identity of witness_map_dev)
+//   G16_WM_PART_FINAL  a <- coset_iNTT(a * b) / (g^n - 1) - c = h   (:187,201-210)
+// Running all four in this order is witness_map_dev(LIBSNARK) bit for bit (same kernels, same tables).
+int witness_map_part_dev(g16_ctx* ctx, int parts, cudaStream_t st) {
+    if (!ctx->have_r1cs) return set_err(ctx, G16_ERR_BAD_ARG, "witness_map_part: no R1CS loaded");
+    NttTables* t;
+    G16_TRY(ntt_get_tables(ctx, ctx->log_n, &t));
+    if (!t->zinv_ok) return set_err(ctx, G16_ERR_VANISHING_ZERO, "g^n - 1 == 0");
+    const size_t n = (size_t)1 << ctx->log_n;
+    const unsigned lr = ctx->log_n;
+    Fr *a = ctx->d_a, *b = ctx->d_b, *c = ctx->d_c;
+    const unsigned pb = (unsigned)((n - ctx->nc + 127) / 128);
+    if (parts & G16_WM_PART_A) {
+        G16_TRY(r1cs_eval_dev(ctx, a, nullptr, nullptr, true, st));
+        G16_LAUNCH(ctx, k_pad_rows, pb, 128, 0, st, ctx->d_z, a, (Fr*)nullptr, (Fr*)nullptr, ctx->nc, ctx->ni, (uint64_t)n, lr);
+        G16_TRY(ntt_dit(ctx, a, t, true, nullptr, nullptr, st));
+        G16_TRY(ntt_dif(ctx, a, t, false, t->coset_scaled, st));
+    }
+    if (parts & G16_WM_PART_B) {
+        G16_TRY(r1cs_eval_dev(ctx, nullptr, b, nullptr, true, st));
+        G16_LAUNCH(ctx, k_pad_rows, pb, 128, 0, st, ctx->d_z, (Fr*)nullptr, b, (Fr*)nullptr, ctx->nc, ctx->ni, (uint64_t)n, lr);
+        G16_TRY(ntt_dit(ctx, b, t, true, nullptr, nullptr, st));
+        G16_TRY(ntt_dif(ctx, b, t, false, t->coset_scaled, st));
+    }
+    if (parts & G16_WM_PART_C) {
+        G16_TRY(r1cs_eval_dev(ctx, nullptr, nullptr, c, true, st));
+        G16_LAUNCH(ctx, k_pad_rows, pb, 128, 0, st, ctx->d_z, (Fr*)nullptr, (Fr*)nullptr, c, ctx->nc, ctx->ni, (uint64_t)n, lr);
+        G16_TRY(ntt_dit(ctx, c, t, true, nullptr, &t->zinv_n, st));
+    }
+    if (parts & G16_WM_PART_FINAL) G16_TRY(ntt_dit(ctx, a, t, true, t->coset_inv_z, nullptr, st, b, c));
     return G16_OK;
 }
 

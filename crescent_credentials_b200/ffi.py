@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("G16_LIB", os.path.join(_HERE, "libg16b200.so"))  # G1
 G16_OK = 0
 ERR_DEGREE_TOO_LARGE, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_VANISHING_ZERO = 1, 2, 3, 4, 5, 6
 REDUCTION_LIBSNARK, REDUCTION_CIRCOM = 0, 1
+WM_PART_A, WM_PART_B, WM_PART_C, WM_PART_FINAL = 1, 2, 4, 8
 ENC_MONTGOMERY, ENC_CANONICAL = 0, 1
 FIELD_FR, FIELD_FQ, FIELD_FQ2 = 0, 1, 2
 OP_MUL, OP_ADD, OP_SUB, OP_NEG, OP_INV, OP_TO_MONT, OP_FROM_MONT, OP_SQR, OP_MUL_BCAST, OP_ADD_BCAST = range(10)
@@ -30,7 +31,7 @@ EXPORTS = [
     "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count", "g16_set_option",
     "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare", "g16_get_msm_stats", "g16_ctx_load_pk_ranges",
     "g16_prove_shard_begin_dev", "g16_prove_shard_finish_dev", "g16_copy_h_dev",
-    "g16_upload_witness_async", "g16_upload_witness_dev", "g16_memcpy_h2d_async", "g16_msm_copy_result_dev", "g16_msm_combine_dev", "g16_graph_stats",
+    "g16_witness_map_part_dev", "g16_wm_vector_copy_dev", "g16_upload_witness_async", "g16_upload_witness_dev", "g16_memcpy_h2d_async", "g16_msm_copy_result_dev", "g16_msm_combine_dev", "g16_graph_stats",
     "g16_ctx_load_vk", "g16_vk_alpha_beta", "g16_prepare_inputs", "g16_verify_batch", "g16_verify_batch_prepared",
     "g16_verify_batch_dev", "g16_pairing", "g16_host_alloc", "g16_host_free",
 ]
@@ -128,6 +129,8 @@ def load_library() -> C.CDLL:
     lib.g16_upload_witness_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.g16_upload_witness_dev.argtypes = [C.c_void_p, C.c_void_p]
     lib.g16_memcpy_h2d_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.g16_witness_map_part_dev.argtypes = [C.c_void_p, C.c_int]
+    lib.g16_wm_vector_copy_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
     lib.g16_prove_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ProofOut)]
     lib.g16_prove_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Partial)]
     lib.g16_prove_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ProofOut)]
@@ -479,6 +482,14 @@ class Context:
     def prove_shard_finish_dev(self, h_dev: int = 0, h_first: int = 0, h_count: int = 0):
         """h_dev: device pointer holding h[h_first, h_first + h_count) (0 = this context's own witness-map output)."""
         self.check(self.lib.g16_prove_shard_finish_dev(self.h, C.c_void_p(h_dev) if h_dev else None, h_first, h_count))
+
+    def witness_map_part_dev(self, parts: int):
+        """LibsnarkReduction witness map in parts (mask of WM_PART_*), stream-ordered; the whole witness must be resident."""
+        self.check(self.lib.g16_witness_map_part_dev(self.h, int(parts)))
+
+    def wm_vector_copy_dev(self, which: int, ext_dev: int, capacity_elems: int, to_ctx: bool):
+        """Copies the context's a (0), b (1) or c (2) vector from / to caller-owned device memory (stream-ordered)."""
+        self.check(self.lib.g16_wm_vector_copy_dev(self.h, which, C.c_void_p(ext_dev), capacity_elems, int(to_ctx)))
 
     def copy_h_dev(self, dst_dev: int, capacity_elems: int):
         self.check(self.lib.g16_copy_h_dev(self.h, C.c_void_p(dst_dev), capacity_elems))

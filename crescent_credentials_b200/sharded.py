@@ -40,6 +40,7 @@ class ShardPlan:
     h_chunk: int                       # staggered: h coefficients per rank in the scatter (equal chunks)
     h_ranges: List[Tuple[int, int]]    # per rank [lo, hi) of h_query
     z_ranges: List[Tuple[int, int]]    # per rank [lo, hi) of a_query[1..] / b_g1_query[1..] / b_g2_query[1..]
+    wm2_rank: int = -1                 # "wm_split": this rank runs the b and c pipelines of the witness map for wm_rank
 
     @property
     def staggered(self) -> bool:
@@ -59,15 +60,28 @@ def rank0_wire_share(world: int, wm_over_z: float = WM_OVER_Z) -> float:
     return max(0.0, (per_other - wm_over_z) / (1.0 + per_other))
 
 
-def staggered_plan(h_len: int, m1: int, world: int, rank0_share: Optional[float] = None) -> ShardPlan:
+WM_SPLIT_MIN_WORLD = 6   # from this many ranks on, two of them carry the witness map between them and no wire MSMs
+
+
+def staggered_plan(h_len: int, m1: int, world: int, rank0_share: Optional[float] = None,
+                   wm_split: Optional[bool] = None) -> ShardPlan:
+    """wm_split (default: world >= 6): at 8 ranks the critical path of a proof is rank 0's unsharded witness map (3.2 ms) +
+    the scatter + a 1.6 ms h MSM, while ranks 1..7 finish their wire MSMs in ~4 ms.  The a, b and c pipelines of the map are
+    independent until the last transform, so rank 1 gives up its wire MSMs too and computes the b and c pipelines while rank 0
+    computes a; b and c cross NVLink (2 x 32 n bytes, point to point) and rank 0 runs the final transform: ~2.3 ms to h."""
     if world == 1:
         return uniform_plan(h_len, m1, 1)
+    split = (world >= WM_SPLIT_MIN_WORLD) if wm_split is None else bool(wm_split) and world >= 3
+    chunk = -(-h_len // world)
+    h = [(min(r * chunk, h_len), min((r + 1) * chunk, h_len)) for r in range(world)]
+    if split and rank0_share is None:
+        nw = world - 2   # wire ranks 2 .. world - 1
+        z = [(0, 0), (0, 0)] + [(m1 * k // nw, m1 * (k + 1) // nw) for k in range(nw)]
+        return ShardPlan(world, 0, chunk, h, z, wm2_rank=1)
     f0 = rank0_wire_share(world) if rank0_share is None else min(max(float(rank0_share), 0.0), 1.0)
     cut = int(round(m1 * f0))
     rest = m1 - cut
     z = [(0, cut)] + [(cut + rest * (r - 1) // (world - 1), cut + rest * r // (world - 1)) for r in range(1, world)]
-    chunk = -(-h_len // world)
-    h = [(min(r * chunk, h_len), min((r + 1) * chunk, h_len)) for r in range(world)]
     return ShardPlan(world, 0, chunk, h, z)
 
 
@@ -133,30 +147,37 @@ class ShardedProver:
                 if rank == self.plan.wm_rank:
                     self.h_all = torch.zeros((cap, 4), dtype=torch.int64, device=dev)
                 self.h_mine = torch.zeros((self.plan.h_chunk, 4), dtype=torch.int64, device=dev)
-            # gathered upload (staggered plan): every rank's 1/G chunk of z, and the assembled vector on the witness-map rank
+            # gathered upload (staggered plan): every rank's 1/G chunk of z and the assembled vector
             self.gather_upload = bool(gather_upload) and world > 1 and self.plan.staggered
             self.z_chunk_len = -(-m // world)
             self.z_chunk = self.z_all = None
             if self.gather_upload:
                 self.z_chunk = torch.zeros((self.z_chunk_len, 4), dtype=torch.int64, device=dev)
-                if rank == self.plan.wm_rank:
-                    self.z_all = torch.zeros((world * self.z_chunk_len, 4), dtype=torch.int64, device=dev)
+                self.z_all = torch.zeros((world * self.z_chunk_len, 4), dtype=torch.int64, device=dev)
+            # wm_split: the b and c vectors travel rank wm2 -> rank wm through these
+            self.vb = self.vc = None
+            if self.plan.wm2_rank >= 0 and rank in (self.plan.wm_rank, self.plan.wm2_rank):
+                n = self.ctx.domain_size()
+                self.vb = torch.zeros((n, 4), dtype=torch.int64, device=dev)
+                self.vc = torch.zeros((n, 4), dtype=torch.int64, device=dev)
         self.stream.synchronize()
         self.z_pin = None          # page-locked staging of the witness for prove()
         self._z_done = None        # event: the last upload from z_pin has been consumed
 
     @property
     def runs_witness_map(self) -> bool:
-        return (not self.plan.staggered) or self.rank == self.plan.wm_rank
+        """True on a rank that needs the WHOLE witness on its device."""
+        return (not self.plan.staggered) or self.rank in (self.plan.wm_rank, self.plan.wm2_rank)
 
     def upload_witness(self, z_host):
         """Stream-ordered upload of the witness (the same z on every rank).  z_host: a page-locked host ADDRESS (int) of m x 4
         u64 words that stays valid until the proof is done, or a numpy array (staged through an internal page-locked buffer).
 
-        Staggered plan: a rank that does not run the witness map uploads only the slice of z its wire MSMs read.  The rank that
-        does run it needs all of z -- 32 m bytes over ONE PCIe link would sit at the head of its critical path (46 MB: 0.8 ms
-        for S-rs256) -- so every rank uploads 1/G of z over its own link and one NCCL gather over NVLink assembles the vector on
-        that rank (`gather_upload`, default on for G > 1).  Uniform plan: every rank runs the witness map and uploads all of z."""
+        Staggered plan: the rank that runs the witness map needs all of z -- 32 m bytes over ONE PCIe link would sit at the head
+        of its critical path (46 MB: 0.8 ms for S-rs256) -- so every rank uploads 1/G of z over its own link and one NCCL
+        all_gather over NVLink assembles the vector on every rank (`gather_upload`, default on for G > 1; 2.07 -> 0.5 ms
+        between the device-timed and the end-to-end proof at 8 GPUs).  Without it, a rank that does not run the witness map
+        uploads only the slice of z its wire MSMs read.  Uniform plan: every rank runs the map and uploads all of z."""
         torch = self.torch
         if isinstance(z_host, np.ndarray):
             z = np.ascontiguousarray(z_host, dtype=np.uint64).reshape(-1, 4)
@@ -181,12 +202,8 @@ class ShardedProver:
             with torch.cuda.stream(self.stream):
                 if cnt:   # my 1/G of z over my own PCIe link (a raw pinned address: copy through the runtime on this stream)
                     ffi.memcpy_h2d_async(self.z_chunk.data_ptr(), addr + lo * 32, cnt * 32, self.stream.cuda_stream)
-                owner = self.rank == self.plan.wm_rank
-                dist.gather(self.z_chunk.view(-1), list(self.z_all.view(self.world, -1)) if owner else None, dst=self.plan.wm_rank)
-                if owner:
-                    self.ctx.upload_witness_dev(self.z_all.data_ptr())
-            if not self.runs_witness_map:
-                self.ctx.upload_witness_async(addr, shard_only=True)
+                dist.all_gather_into_tensor(self.z_all.view(-1), self.z_chunk.view(-1))   # 32 m bytes per rank over NVLink
+                self.ctx.upload_witness_dev(self.z_all.data_ptr())
         else:
             self.ctx.upload_witness_async(addr, shard_only=not self.runs_witness_map)
         if isinstance(z_host, np.ndarray):
@@ -202,7 +219,24 @@ class ShardedProver:
                 ctx.prove_prepare(rr, ss)   # overlaps r*delta, s*delta, ... with the shard MSMs
             if plan.staggered:
                 owner = rank == plan.wm_rank
-                ctx.prove_shard_begin_dev(rr, ss, reduction, run_witness_map=owner)
+                split = plan.wm2_rank >= 0 and reduction == ffi.REDUCTION_LIBSNARK
+                ctx.prove_shard_begin_dev(rr, ss, reduction, run_witness_map=owner and not split)
+                if split and owner:          # a pipeline here, b and c arrive from the helper, then the last transform
+                    n = self.vb.shape[0]
+                    ctx.witness_map_part_dev(ffi.WM_PART_A)
+                    dist.recv(self.vb.view(-1), src=plan.wm2_rank)
+                    ctx.wm_vector_copy_dev(1, self.vb.data_ptr(), n, to_ctx=True)
+                    dist.recv(self.vc.view(-1), src=plan.wm2_rank)
+                    ctx.wm_vector_copy_dev(2, self.vc.data_ptr(), n, to_ctx=True)
+                    ctx.witness_map_part_dev(ffi.WM_PART_FINAL)
+                elif split and rank == plan.wm2_rank:
+                    n = self.vb.shape[0]
+                    ctx.witness_map_part_dev(ffi.WM_PART_B)
+                    ctx.wm_vector_copy_dev(1, self.vb.data_ptr(), n, to_ctx=False)
+                    dist.send(self.vb.view(-1), dst=plan.wm_rank)
+                    ctx.witness_map_part_dev(ffi.WM_PART_C)
+                    ctx.wm_vector_copy_dev(2, self.vc.data_ptr(), n, to_ctx=False)
+                    dist.send(self.vc.view(-1), dst=plan.wm_rank)
                 if owner:
                     ctx.copy_h_dev(self.h_all.data_ptr(), self.h_all.shape[0])
                 scatter_h(self.h_all, self.h_mine, plan, rank)   # the one exchange step: n*32/G bytes to every peer

@@ -187,6 +187,17 @@ int g16_copy_partial_dev(g16_ctx* ctx, void* dst_dev);         /* stream-ordered
  * Fr; must cover the rank's h range; NULL = this context's own witness-map output).  begin: forks the wire MSMs (+ witness map); finish: h MSM + join; the partial is then in the device buffer. */
 int g16_prove_shard_begin_dev(g16_ctx* ctx, const uint64_t r[4], const uint64_t s[4], int reduction, int run_witness_map);
 int g16_prove_shard_finish_dev(g16_ctx* ctx, const void* h_dev, size_t h_first, size_t h_count); /* h_dev[i] = h[h_first + i], i < h_count */
+/* The LibsnarkReduction witness map in parts, for host glue that spreads it over several GPUs (the a, b and c pipelines are
+ * independent until the last transform): `parts` is a mask of G16_WM_PART_*; each part reads / leaves its vector in the context
+ * (a: A, FINAL; b: B; c: C), FINAL needs a, b and c and leaves h in a (g16_copy_h_dev).  The whole witness must be on the device.
+ * A | B | C | FINAL in one call equals g16_witness_map's device work bit for bit.  g16_wm_vector_copy_dev moves one of the three
+ * n-element vectors between the context and caller-owned device memory (to_ctx != 0: into the context), stream-ordered. */
+#define G16_WM_PART_A 1
+#define G16_WM_PART_B 2
+#define G16_WM_PART_C 4
+#define G16_WM_PART_FINAL 8
+int g16_witness_map_part_dev(g16_ctx* ctx, int parts);
+int g16_wm_vector_copy_dev(g16_ctx* ctx, int which /* 0 = a, 1 = b, 2 = c */, void* ext_dev, size_t capacity_elems, int to_ctx);
 int g16_copy_h_dev(g16_ctx* ctx, void* dst_dev, size_t capacity_elems); /* stream-ordered D2D copy of h (n elements) */
 /* Optional, rank 0: starts the (r, s, pk)-only scalar multiplications on a side stream so that they overlap the shard work;
  * a later g16_prove_combine[_dev] with the same (r, s) joins them instead of running them serially. */

@@ -27,7 +27,10 @@ def main():
         r, s = int(meta["r"], 16), int(meta["s"], 16)
         h_len = pk.arrays["h_query"].shape[0]
         m1 = pk.arrays["a_query"].shape[0] - 1
-        for plan in (None, sharded.uniform_plan(h_len, m1, world), sharded.staggered_plan(h_len, m1, world, 0.0)):
+        plans = [None, sharded.uniform_plan(h_len, m1, world), sharded.staggered_plan(h_len, m1, world, 0.0)]
+        if world >= 3:   # two ranks carry the witness map between them (b and c pipelines on rank 1, point-to-point to rank 0)
+            plans.append(sharded.staggered_plan(h_len, m1, world, wm_split=True))
+        for plan in plans:
             # default constructor arguments: the class makes its own stream and context (the documented call)
             prover = sharded.ShardedProver(pk, mats, local, rank, world, plan=plan, precompute=(plan is None))
             try:

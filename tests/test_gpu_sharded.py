@@ -131,7 +131,8 @@ def test_sharded_prover_class_over_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
     here = os.path.dirname(os.path.abspath(__file__))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+    ranks = "4" if torch.cuda.device_count() >= 4 else "2"   # 4 ranks also exercise the wm_split plan
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", ranks, "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(here, "sharded_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
@@ -164,3 +165,56 @@ def test_witness_from_device_memory():
         ctx.dev_free(d)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("name", ["rand300", "dummy924_nozk", "silly"])
+def test_witness_map_in_parts_equals_the_whole(name):
+    """g16_witness_map_part_dev: A | B | C | FINAL on one context, and the "wm_split" choreography of sharded.py on two
+    contexts (B and C computed by a helper, carried over with g16_wm_vector_copy_dev, A and FINAL on the owner), both give
+    the h of g16_witness_map bit for bit."""
+    meta, r1cs_bytes, _ = load_golden(name)
+    mats = load_matrices(r1cs_bytes)
+    wires = mats.num_instance_variables + mats.num_witness_variables
+    z = g.fr_to_mont([int(v, 16) for v in meta["z"]])
+    owner, helper = ffi.Context(0), ffi.Context(0)
+    try:
+        for ctx in (owner, helper):
+            ctx.load_r1cs(mats.num_constraints, mats.num_instance_variables, wires, mats.row_ptr, mats.col, mats.val, mats.encoding)
+        n = owner.domain_size()
+        want = owner.witness_map(z, ffi.REDUCTION_LIBSNARK)
+        assert g.fr_from_mont(want) == [int(v, 16) for v in meta["h"]]
+        out = owner.dev_alloc(n * 32)
+        for rep in range(3):   # eager, captured, replayed
+            owner.upload_witness(z)
+            owner.witness_map_part_dev(ffi.WM_PART_A | ffi.WM_PART_B | ffi.WM_PART_C | ffi.WM_PART_FINAL)
+            owner.copy_h_dev(out, n)
+            owner.sync()
+            assert np.array_equal(owner.dev_download(out, np.zeros((n, 4), dtype=np.uint64)), want), rep
+        vb, vc = helper.dev_alloc(n * 32), helper.dev_alloc(n * 32)
+        for rep in range(3):
+            helper.upload_witness(z)
+            owner.upload_witness(z)
+            helper.witness_map_part_dev(ffi.WM_PART_B)
+            helper.wm_vector_copy_dev(1, vb, n, to_ctx=False)
+            helper.witness_map_part_dev(ffi.WM_PART_C)
+            helper.wm_vector_copy_dev(2, vc, n, to_ctx=False)
+            helper.sync()
+            owner.witness_map_part_dev(ffi.WM_PART_A)
+            owner.wm_vector_copy_dev(1, vb, n, to_ctx=True)
+            owner.wm_vector_copy_dev(2, vc, n, to_ctx=True)
+            owner.witness_map_part_dev(ffi.WM_PART_FINAL)
+            owner.copy_h_dev(out, n)
+            owner.sync()
+            assert np.array_equal(owner.dev_download(out, np.zeros((n, 4), dtype=np.uint64)), want), rep
+        with pytest.raises(ffi.G16Error):
+            owner.witness_map_part_dev(0)
+        fresh = ffi.Context(0)
+        try:
+            fresh.load_r1cs(mats.num_constraints, mats.num_instance_variables, wires, mats.row_ptr, mats.col, mats.val, mats.encoding)
+            with pytest.raises(ffi.G16Error):   # no witness on the device
+                fresh.witness_map_part_dev(ffi.WM_PART_A)
+        finally:
+            fresh.close()
+    finally:
+        owner.close()
+        helper.close()
