@@ -248,7 +248,7 @@ class Runner:
         m1 = inst.m - 1
         return {"workload": f"{inst.name} ({args.witness} witness)", "constraints": inst.nc, "wires": inst.m, "domain": inst.n,
                 "nnz": nnz, "parallelism": f"msm-shard{self.world}" if self.world > 1 else "single",
-                "plan": ({"kind": args.plan, "witness_map_rank": plan.wm_rank, "witness_map_bc_rank": plan.wm2_rank, "rank0_wire_share": round(plan.z_ranges[0][1] / max(m1, 1), 4),
+                "plan": ({"kind": args.plan, "witness_map_rank": plan.wm_rank, "witness_map_b_c_ranks": [plan.wm2_rank, plan.wm3_rank], "rank0_wire_share": round(plan.z_ranges[0][1] / max(m1, 1), 4),
                           "h_scatter_bytes_per_peer": plan.h_chunk * 32 if plan.staggered else 0} if self.world > 1 else None),
                 "l2": "inputs>L2 (pk+scratch ~GBs)", "precompute": args.precompute,
                 "window_bits": args.window_bits or "auto (19 at this size)", "ba_levels": args.ba_levels, "synthetic": SYNTH_NOTE}
@@ -295,8 +295,9 @@ def main():
     ap.add_argument("--plan", choices=["staggered", "uniform"], default="staggered",
                     help="N > 1: staggered = only rank 0 runs the witness map, the other ranks take a larger share of the wire "
                          "MSMs and receive their h chunk through one NCCL scatter; uniform = every rank runs the witness map")
-    ap.add_argument("--wm-split", type=int, default=-1, help="staggered plan: 1 / 0 force the split of the witness map over ranks 0 and "
-                    "1 on / off (default -1: on from 6 ranks)")
+    ap.add_argument("--wm-split", type=int, default=-1, help="staggered plan: 1 = the b and c pipelines of the witness map on ranks 1 and 2 "
+                    "(sharded.staggered_plan wm_split); default -1 / 0: the whole map on rank 0")
+    ap.add_argument("--nccl-env", nargs="*", default=[], help="NCCL environment settings applied before init, KEY=VALUE")
     ap.add_argument("--rank0-share", type=float, default=None,
                     help="staggered plan: rank 0's share of the wire MSMs (default: the balance point of sharded.rank0_wire_share)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -330,6 +331,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        for kv in args.nccl_env:   # e.g. NCCL_MIN_P2P_NCHANNELS=16 for the point-to-point transfers of --wm-split 1
+            os.environ[kv.split("=")[0]] = kv.split("=")[1]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # a real (non-default) torch stream is the library's main stream: torch events and NCCL calls are ordered with it
     tstream = torch.cuda.Stream(priority=args.main_priority)

@@ -1115,9 +1115,12 @@ int g16_witness_map_part_dev(g16_ctx* ctx, int parts) {
         const int bit = 1 << k;
         if (!(parts & bit)) continue;
         const bool alone = ctx->wm_alone;
-        G16_TRY(run_graphed(ctx, GR_PART + k, 0x400 + (uint64_t)bit, ctx->main, [&] {
+        bool busy = false;  // wire MSMs beside the transforms? (then the modest radix-2, unbatched launches: see opt_ntt_radix4)
+        if (ctx->have_pk)
+            for (int qi : {Q_L, Q_A, Q_B1, Q_B2}) busy = busy || ctx->sh_hi[qi] > ctx->sh_lo[qi];
+        G16_TRY(run_graphed(ctx, GR_PART + k, 0x400 + (uint64_t)bit * 2 + busy, ctx->main, [&] {
             if (bit == G16_WM_PART_A) G16_TRY(rec_t(ctx, ctx->ev_t[0], ctx->main));
-            ctx->wm_alone = true;  // a rank that runs witness-map parts has no wire MSMs beside them (sharded.py)
+            ctx->wm_alone = !busy;
             int rc = witness_map_part_dev(ctx, bit, ctx->main);
             ctx->wm_alone = alone;
             G16_TRY(rc);

@@ -40,7 +40,8 @@ class ShardPlan:
     h_chunk: int                       # staggered: h coefficients per rank in the scatter (equal chunks)
     h_ranges: List[Tuple[int, int]]    # per rank [lo, hi) of h_query
     z_ranges: List[Tuple[int, int]]    # per rank [lo, hi) of a_query[1..] / b_g1_query[1..] / b_g2_query[1..]
-    wm2_rank: int = -1                 # "wm_split": this rank runs the b and c pipelines of the witness map for wm_rank
+    wm2_rank: int = -1                 # "wm_split": this rank runs the b pipeline of the witness map for wm_rank ...
+    wm3_rank: int = -1                 # ... and this one the c pipeline (both beside their own wire MSMs)
 
     @property
     def staggered(self) -> bool:
@@ -60,29 +61,22 @@ def rank0_wire_share(world: int, wm_over_z: float = WM_OVER_Z) -> float:
     return max(0.0, (per_other - wm_over_z) / (1.0 + per_other))
 
 
-WM_SPLIT_MIN_WORLD = 6   # from this many ranks on, two of them carry the witness map between them and no wire MSMs
-
-
 def staggered_plan(h_len: int, m1: int, world: int, rank0_share: Optional[float] = None,
                    wm_split: Optional[bool] = None) -> ShardPlan:
-    """wm_split (default: world >= 6): at 8 ranks the critical path of a proof is rank 0's unsharded witness map (3.2 ms) +
-    the scatter + a 1.6 ms h MSM, while ranks 1..7 finish their wire MSMs in ~4 ms.  The a, b and c pipelines of the map are
-    independent until the last transform, so rank 1 gives up its wire MSMs too and computes the b and c pipelines while rank 0
-    computes a; b and c cross NVLink (2 x 32 n bytes, point to point) and rank 0 runs the final transform: ~2.3 ms to h."""
+    """wm_split (default off; needs world >= 3): the a, b and c pipelines of the witness map are independent until the last
+    transform, so rank 1 computes the b pipeline and rank 2 the c pipeline beside their own wire MSMs (those chains are
+    latency-bound and leave the multiplier mostly idle), each sends its vector point to point over NVLink (32 n bytes) and rank 0
+    -- which computes the a pipeline meanwhile -- runs the last transform.  Measured at 8 GPUs in DESIGN.md section 4."""
     if world == 1:
         return uniform_plan(h_len, m1, 1)
-    split = (world >= WM_SPLIT_MIN_WORLD) if wm_split is None else bool(wm_split) and world >= 3
-    chunk = -(-h_len // world)
-    h = [(min(r * chunk, h_len), min((r + 1) * chunk, h_len)) for r in range(world)]
-    if split and rank0_share is None:
-        nw = world - 2   # wire ranks 2 .. world - 1
-        z = [(0, 0), (0, 0)] + [(m1 * k // nw, m1 * (k + 1) // nw) for k in range(nw)]
-        return ShardPlan(world, 0, chunk, h, z, wm2_rank=1)
+    split = bool(wm_split) and world >= 3
     f0 = rank0_wire_share(world) if rank0_share is None else min(max(float(rank0_share), 0.0), 1.0)
     cut = int(round(m1 * f0))
     rest = m1 - cut
     z = [(0, cut)] + [(cut + rest * (r - 1) // (world - 1), cut + rest * r // (world - 1)) for r in range(1, world)]
-    return ShardPlan(world, 0, chunk, h, z)
+    chunk = -(-h_len // world)
+    h = [(min(r * chunk, h_len), min((r + 1) * chunk, h_len)) for r in range(world)]
+    return ShardPlan(world, 0, chunk, h, z, wm2_rank=1 if split else -1, wm3_rank=2 if split else -1)
 
 
 def gather_partials(mine, world: int):
@@ -154,12 +148,14 @@ class ShardedProver:
             if self.gather_upload:
                 self.z_chunk = torch.zeros((self.z_chunk_len, 4), dtype=torch.int64, device=dev)
                 self.z_all = torch.zeros((world * self.z_chunk_len, 4), dtype=torch.int64, device=dev)
-            # wm_split: the b and c vectors travel rank wm2 -> rank wm through these
+            # wm_split: the b and c vectors travel from ranks wm2 / wm3 to rank wm through these
             self.vb = self.vc = None
-            if self.plan.wm2_rank >= 0 and rank in (self.plan.wm_rank, self.plan.wm2_rank):
+            if self.plan.wm2_rank >= 0 and rank in (self.plan.wm_rank, self.plan.wm2_rank, self.plan.wm3_rank):
                 n = self.ctx.domain_size()
-                self.vb = torch.zeros((n, 4), dtype=torch.int64, device=dev)
-                self.vc = torch.zeros((n, 4), dtype=torch.int64, device=dev)
+                if rank in (self.plan.wm_rank, self.plan.wm2_rank):
+                    self.vb = torch.zeros((n, 4), dtype=torch.int64, device=dev)
+                if rank in (self.plan.wm_rank, self.plan.wm3_rank):
+                    self.vc = torch.zeros((n, 4), dtype=torch.int64, device=dev)
         self.stream.synchronize()
         self.z_pin = None          # page-locked staging of the witness for prove()
         self._z_done = None        # event: the last upload from z_pin has been consumed
@@ -167,7 +163,7 @@ class ShardedProver:
     @property
     def runs_witness_map(self) -> bool:
         """True on a rank that needs the WHOLE witness on its device."""
-        return (not self.plan.staggered) or self.rank in (self.plan.wm_rank, self.plan.wm2_rank)
+        return (not self.plan.staggered) or self.rank in (self.plan.wm_rank, self.plan.wm2_rank, self.plan.wm3_rank)
 
     def upload_witness(self, z_host):
         """Stream-ordered upload of the witness (the same z on every rank).  z_host: a page-locked host ADDRESS (int) of m x 4
@@ -221,19 +217,21 @@ class ShardedProver:
                 owner = rank == plan.wm_rank
                 split = plan.wm2_rank >= 0 and reduction == ffi.REDUCTION_LIBSNARK
                 ctx.prove_shard_begin_dev(rr, ss, reduction, run_witness_map=owner and not split)
-                if split and owner:          # a pipeline here, b and c arrive from the helper, then the last transform
+                if split and owner:          # a pipeline here, b and c arrive from the helpers, then the last transform
                     n = self.vb.shape[0]
                     ctx.witness_map_part_dev(ffi.WM_PART_A)
+                    dist.recv(self.vc.view(-1), src=plan.wm3_rank)   # c is ready first (one transform)
+                    ctx.wm_vector_copy_dev(2, self.vc.data_ptr(), n, to_ctx=True)
                     dist.recv(self.vb.view(-1), src=plan.wm2_rank)
                     ctx.wm_vector_copy_dev(1, self.vb.data_ptr(), n, to_ctx=True)
-                    dist.recv(self.vc.view(-1), src=plan.wm2_rank)
-                    ctx.wm_vector_copy_dev(2, self.vc.data_ptr(), n, to_ctx=True)
                     ctx.witness_map_part_dev(ffi.WM_PART_FINAL)
                 elif split and rank == plan.wm2_rank:
                     n = self.vb.shape[0]
                     ctx.witness_map_part_dev(ffi.WM_PART_B)
                     ctx.wm_vector_copy_dev(1, self.vb.data_ptr(), n, to_ctx=False)
                     dist.send(self.vb.view(-1), dst=plan.wm_rank)
+                elif split and rank == plan.wm3_rank:
+                    n = self.vc.shape[0]
                     ctx.witness_map_part_dev(ffi.WM_PART_C)
                     ctx.wm_vector_copy_dev(2, self.vc.data_ptr(), n, to_ctx=False)
                     dist.send(self.vc.view(-1), dst=plan.wm_rank)

@@ -28,7 +28,7 @@ def main():
         h_len = pk.arrays["h_query"].shape[0]
         m1 = pk.arrays["a_query"].shape[0] - 1
         plans = [None, sharded.uniform_plan(h_len, m1, world), sharded.staggered_plan(h_len, m1, world, 0.0)]
-        if world >= 3:   # two ranks carry the witness map between them (b and c pipelines on rank 1, point-to-point to rank 0)
+        if world >= 3:   # the b and c pipelines of the witness map on ranks 1 and 2, point-to-point to rank 0
             plans.append(sharded.staggered_plan(h_len, m1, world, wm_split=True))
         for plan in plans:
             # default constructor arguments: the class makes its own stream and context (the documented call)
