@@ -21,4 +21,4 @@ timeout 900 ncu --profile-from-start off --set full --import-source on --clock-c
   -k regex:'k_ba_add|k_ba_products|k_ba_invert|k_ntt_pass4|k_spmv_sell|k_chunk_reduce|k_bucket_tail|k_rs_scatter' -f -o gpurun_out/ncu_r02_all \
   python tools/prof_prove.py --precompute 1 --serialize 1 --reps 1 > gpurun_out/ncu_r02_all.log 2>&1; echo "ncu full rc=$? $((SECONDS-t0))s"
 python tools/ncu_summary.py gpurun_out/ncu_r02_all.ncu-rep > gpurun_out/ncu_r02_all.txt 2>&1; ls -la gpurun_out/ncu_r02_all.ncu-rep
-bash tools/gpu_ab_mul3.sh; echo "ab rc=$? $((SECONDS-t0))s"
+# (round 2, pass 1 also ran the A/B of the -DG16_FQ2_MUL3 build here: slower on both counts, script and variant removed)
