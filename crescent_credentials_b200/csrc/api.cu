@@ -904,16 +904,23 @@ static int shard_begin(g16_ctx* ctx, int reduction, bool run_wm, bool allow_hi =
     bool busy = false;
     for (int qi : {Q_L, Q_A, Q_B1, Q_B2}) busy = busy || ctx->sh_hi[qi] > ctx->sh_lo[qi];
     cudaStream_t wire = ctx->opt_serialize ? main : ctx->wire;
-    if (wire != main) {
-        G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
-        G16_CUDA(ctx, cudaStreamWaitEvent(wire, ctx->ev_fork, 0));
-    }
-    G16_TRY(run_graphed(ctx, GR_WIRE, 0x57, wire, [&] { return queue_wire_chains(ctx, wire); }));
-    if (wire != main) G16_CUDA(ctx, cudaEventRecord(ctx->ev_wire_done, wire));
+    // option wm_first: the witness map runs first and alone, the wire chains start when it is done, so that all five MSM
+    // chains run (and end) together instead of the h MSM finishing alone behind the others
+    const bool wm_first = run_wm && ctx->opt_wm_first && !ctx->opt_serialize && busy;
+    auto start_wire = [&]() -> int {
+        if (wire != main) {
+            G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
+            G16_CUDA(ctx, cudaStreamWaitEvent(wire, ctx->ev_fork, 0));
+        }
+        G16_TRY(run_graphed(ctx, GR_WIRE, 0x57, wire, [&] { return queue_wire_chains(ctx, wire); }));
+        if (wire != main) G16_CUDA(ctx, cudaEventRecord(ctx->ev_wire_done, wire));
+        return G16_OK;
+    };
+    if (!wm_first) G16_TRY(start_wire());
     // main: witness map (r1cs_to_qap.rs:150-213)
     // (option wm_priority: on the high-priority twin of main, so that the h MSM -- which can only start afterwards -- is not
     // pushed to the end of the proof by the four z-only MSMs already in flight)
-    cudaStream_t ws = (allow_hi && run_wm && ctx->opt_wm_priority && !ctx->opt_serialize && ctx->hi) ? ctx->hi : main;
+    cudaStream_t ws = (allow_hi && run_wm && ctx->opt_wm_priority && !ctx->opt_serialize && !wm_first && ctx->hi) ? ctx->hi : main;
     ctx->sh_wm_stream = ws;
     if (ws != main) {
         G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
@@ -921,7 +928,7 @@ static int shard_begin(g16_ctx* ctx, int reduction, bool run_wm, bool allow_hi =
     }
     if (run_wm) {
         // transforms beside MSM chains use the radix-2 passes, a lone witness map the radix-4 ones (see opt_ntt_radix4)
-        const bool alone = ctx->opt_serialize || !busy;
+        const bool alone = ctx->opt_serialize || !busy || wm_first;
         G16_TRY(run_graphed(ctx, GR_WM, 0x100 + (uint64_t)reduction * 2 + alone, ws, [&] {
             G16_TRY(rec_t(ctx, ctx->ev_t[0], ws));
             ctx->wm_alone = alone;
@@ -934,6 +941,7 @@ static int shard_begin(g16_ctx* ctx, int reduction, bool run_wm, bool allow_hi =
         G16_TRY(rec_t(ctx, ctx->ev_t[0], ws));
         G16_TRY(rec_t(ctx, ctx->ev_t[1], ws));
     }
+    if (wm_first) G16_TRY(start_wire());
     return G16_OK;
 }
 
@@ -1249,6 +1257,7 @@ int g16_set_option(g16_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "spmv_sell")) ctx->opt_spmv_sell = value;
     else if (!strcmp(key, "ntt_batch")) ctx->opt_ntt_batch = value;
     else if (!strcmp(key, "wm_priority")) ctx->opt_wm_priority = value;
+    else if (!strcmp(key, "wm_first")) ctx->opt_wm_first = value;
     else if (!strcmp(key, "verify_occupancy")) ctx->opt_verify_occupancy = value;
     else if (!strcmp(key, "asm_tables")) ctx->opt_asm_tables = value;
     else return set_err(ctx, G16_ERR_BAD_ARG, "unknown option '%s'", key);

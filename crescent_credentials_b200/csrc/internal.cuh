@@ -188,6 +188,7 @@ struct g16_ctx {
     bool wm_alone = true;      // state of the auto choice for the transforms being queued right now
     int opt_split_chains = 1;  // the MSM that reuses a digit stage runs beside the one that built it, not after it
     int opt_wm_priority = 0;   // witness map + h MSM on the internal high-priority stream
+    int opt_wm_first = 0;      // the wire MSM chains start only when the witness map is done (it then runs alone)
     cudaStream_t hi = nullptr;  // high-priority twin of main
     cudaEvent_t ev_dig[2] = {}, ev_hi = nullptr;
     bool share_al = false, share_b = false;  // l reuses a's digit stage / b_g2 reuses b_g1's

@@ -313,7 +313,7 @@ def test_golden_prove_digit_sharing(share, levels):
             prover.close()
 
 
-@pytest.mark.parametrize("split,prio", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("split,prio", [(0, 0), (1, 0), (0, 1), (1, 1), (1, 2), (1, 3)])
 def test_golden_prove_stream_plans(split, prio):
     """Where the MSMs are queued (the digit-sharing MSM beside / behind the one that built the stage; witness map + h MSM on
     the high-priority stream) changes the order of execution only: same proof bytes, also when proofs run back to back."""
@@ -324,7 +324,8 @@ def test_golden_prove_stream_plans(split, prio):
         prover = g.Groth16(0, precompute=True)
         prover.ctx.set_option("share_digits", 1)
         prover.ctx.set_option("split_chains", split)
-        prover.ctx.set_option("wm_priority", prio)
+        prover.ctx.set_option("wm_priority", min(prio, 2))   # 2: only the witness map on the high-priority stream
+        prover.ctx.set_option("wm_first", int(prio == 3))     # 3: the wire chains start after the witness map
         try:
             z = [int(v, 16) for v in meta["z"]]
             for _ in range(3):
