@@ -16,6 +16,7 @@
 // k_scale_point computes s*MSM_a / r*MSM_b1 (per rank, on the MSM's own stream) as soon as that MSM is done, while the
 // other MSMs are still running; k_assemble_post only adds (summing over the `count` shard partials) and normalises.
 #include "internal.cuh"
+#include "glv.cuh"
 
 namespace g16 {
 
@@ -42,6 +43,7 @@ struct AsmScalars {
     Scalar256 r, s, rs;
     int r_is_zero;
     int pad[7];
+    GlvScalar glv[2];  // GLV splits of r (0) and s (1) for k_scale_point
 };
 
 __global__ void k_assemble_pre(AsmConsts k, const AsmScalars* __restrict__ sc, AsmPre* out) {
@@ -176,10 +178,28 @@ __global__ void __launch_bounds__(160) k_assemble_pre_tables(const AsmTables* __
 }
 
 // out = k * in for one G1 point (one lane; latency-bound, runs beside the remaining MSMs)
-__global__ void k_scale_point(const G1XYZZ* __restrict__ in, const Scalar256* __restrict__ k, G1XYZZ* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const Scalar256 kk = *k;
-        *out = scalar_mul_window(*in, kk.w);
+// out = k * in for one G1 point (latency-bound, runs beside the remaining MSMs; exposed at the very end of a proof when the a /
+// b_g1 MSMs are the last to finish).  Two warps, one lane each: k = k1 + k2 * lambda, warp 0 computes k1 * P, warp 1 k2 * phi(P)
+// (glv.cuh), lane 0 adds.  `which` = 0: k = r, 1: k = s.
+__global__ void __launch_bounds__(64) k_scale_point(const G1XYZZ* __restrict__ in, const AsmScalars* __restrict__ sc, int which,
+                                                    G1XYZZ* __restrict__ out) {
+    __shared__ G1XYZZ half[2];
+    const unsigned w = threadIdx.x >> 5;
+    const GlvScalar& g = sc->glv[which];
+    if ((threadIdx.x & 31) == 0) {
+        if (g.ok) {
+            half[w] = glv_half_mul(*in, g.h[w], (int)w);
+        } else if (w == 0) {  // magnitudes out of range (not observed): plain windowed multiplication
+            const Scalar256 kk = which == 0 ? sc->r : sc->s;
+            half[0] = scalar_mul_window(*in, kk.w);
+            half[1] = G1XYZZ::inf();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        G1XYZZ r = half[0];
+        r.add_inl(half[1]);
+        *out = r;
     }
 }
 
@@ -270,6 +290,8 @@ int assemble_set_scalars(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, cud
     h->s = canon(sm);
     h->rs = canon(rs);
     h->r_is_zero = (int)rm.is_zero();
+    h->glv[0] = glv_decompose(h->r.w);
+    h->glv[1] = glv_decompose(h->s.w);
     G16_CUDA(ctx, cudaMemcpyAsync(scalars_ptr(ctx), h, sizeof(AsmScalars), cudaMemcpyHostToDevice, st));
     return G16_OK;
 }
@@ -294,8 +316,7 @@ int assemble_pre(g16_ctx* ctx, cudaStream_t st) {
 
 // which = 0: k = r, 1: k = s (of the scalars assemble_set_scalars put on the device)
 int scale_point_dev(g16_ctx* ctx, const void* in_xyzz, int which, void* out_xyzz, cudaStream_t st) {
-    const Scalar256* k = which == 0 ? &scalars_ptr(ctx)->r : &scalars_ptr(ctx)->s;
-    G16_LAUNCH(ctx, k_scale_point, 1, 32, 0, st, (const G1XYZZ*)in_xyzz, k, (G1XYZZ*)out_xyzz);
+    G16_LAUNCH(ctx, k_scale_point, 1, 64, 0, st, (const G1XYZZ*)in_xyzz, (const AsmScalars*)scalars_ptr(ctx), which, (G1XYZZ*)out_xyzz);
     return G16_OK;
 }
 

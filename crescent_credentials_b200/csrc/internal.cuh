@@ -189,6 +189,8 @@ struct g16_ctx {
     int opt_split_chains = 1;  // the MSM that reuses a digit stage runs beside the one that built it, not after it
     int opt_wm_priority = 0;   // witness map + h MSM on the internal high-priority stream
     int opt_wm_first = 0;      // the wire MSM chains start only when the witness map is done (it then runs alone)
+    int opt_chain_priority = 0;  // the a and b_g1 chains on high-priority streams (their results still need the scaling kernel)
+    cudaStream_t prio[2] = {};
     cudaStream_t hi = nullptr;  // high-priority twin of main
     cudaEvent_t ev_dig[2] = {}, ev_hi = nullptr;
     bool share_al = false, share_b = false;  // l reuses a's digit stage / b_g2 reuses b_g1's

@@ -124,6 +124,37 @@ def test_windowed_scalar_mul_on_host_matches_oracle(host_fp):
         assert outs[0] == want and outs[1] == want, hex(k)
 
 
+def test_glv_split_on_host_matches_oracle(host_fp):
+    """glv.cuh: the constants (beta, lambda, the lattice basis behind the rounding constants), the decomposition
+    k = k1 + k2 * lambda (mod r) with short halves, and k * P = k1 * P + k2 * phi(P) against the oracle (what k_scale_point runs)."""
+    r, q = o.R_MOD, o.Q_MOD
+    beta = 0x59e26bcea0d48bacd4f263f1acdb5c4f5763473177fffffe
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    assert pow(beta, 3, q) == 1 and beta != 1 and pow(lam, 3, r) == 1 and lam != 1
+    P = o.G1.mul(o.G1_GEN, 0xC0FFEE1234567)
+    assert o.G1.mul(P, lam) == (beta * P[0] % q, P[1])                      # phi(P) = lambda * P
+    rnd = random.Random(10)
+    ks = [0, 1, 2, r - 1, r - 2, lam, r - lam, r // 2, 1 << 253, (1 << 128) - 1, 1 << 128] + [rnd.randrange(r) for _ in range(3000)]
+    for k in ks:
+        K = ctypes.create_string_buffer(k.to_bytes(32, "little"), 32)
+        out = (ctypes.c_uint32 * 13)()
+        host_fp.host_glv_decompose(K, out)
+        k1 = sum(out[i] << (32 * i) for i in range(5)) * (-1 if out[5] else 1)
+        k2 = sum(out[6 + i] << (32 * i) for i in range(5)) * (-1 if out[11] else 1)
+        assert out[12] == 1 and abs(k1) < 1 << 128 and abs(k2) < 1 << 128, hex(k)
+        assert (k1 + k2 * lam) % r == k, hex(k)
+    enc = lambda Pt: b"".join(((v << 256) % q).to_bytes(32, "little") for v in Pt)
+    rinv = pow(1 << 256, -1, q)
+    for k in ks[:11] + ks[-20:]:
+        A = ctypes.create_string_buffer(enc(P), 64)
+        K = ctypes.create_string_buffer(k.to_bytes(32, "little"), 32)
+        R = ctypes.create_string_buffer(64)
+        host_fp.host_g1_scalar_mul_glv(A, K, R)
+        x, y = (int.from_bytes(R.raw[i:i + 32], "little") * rinv % q for i in (0, 32))
+        got = None if x == 0 and y == 0 else (x, y)
+        assert got == o.G1.to_affine(o.G1.jmul(o.G1.to_jac(P), k)), hex(k)
+
+
 def test_device_fq2_code_on_host_matches_oracle(host_fp):
     rnd = random.Random(2)
     enc = lambda x: b"".join(((v << 256) % o.Q_MOD).to_bytes(32, "little") for v in x)
