@@ -917,7 +917,10 @@ static int shard_begin(g16_ctx* ctx, int reduction, bool run_wm, bool allow_hi =
     cudaStream_t wire = ctx->opt_serialize ? main : ctx->wire;
     // option wm_first: the witness map runs first and alone, the wire chains start when it is done, so that all five MSM
     // chains run (and end) together instead of the h MSM finishing alone behind the others
-    const bool wm_first = run_wm && ctx->opt_wm_first && !ctx->opt_serialize && busy;
+    // (measured: S-rs256 29.0 -> 28.2 ms; S-2^12 1.86 -> 2.16 ms and S-2^16 3.06 -> 3.43 ms, where the map is a fraction of a
+    // millisecond and delaying the chains only adds latency -- hence automatic from n = 2^20 on: profiles/r02_ab_sched2_glv.log)
+    const bool want_first = ctx->opt_wm_first < 0 ? ctx->log_n >= 20 : ctx->opt_wm_first != 0;
+    const bool wm_first = run_wm && want_first && !ctx->opt_serialize && busy;
     auto start_wire = [&]() -> int {
         if (wire != main) {
             G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));

@@ -188,7 +188,8 @@ struct g16_ctx {
     bool wm_alone = true;      // state of the auto choice for the transforms being queued right now
     int opt_split_chains = 1;  // the MSM that reuses a digit stage runs beside the one that built it, not after it
     int opt_wm_priority = 0;   // witness map + h MSM on the internal high-priority stream
-    int opt_wm_first = 0;      // the wire MSM chains start only when the witness map is done (it then runs alone)
+    int opt_wm_first = -1;     // the wire MSM chains start only when the witness map is done (it then runs alone);
+                               // -1 = auto: for domains of 2^20 and more, 0 / 1 force
     int opt_chain_priority = 0;  // the a and b_g1 chains on high-priority streams (their results still need the scaling kernel)
     cudaStream_t prio[2] = {};
     cudaStream_t hi = nullptr;  // high-priority twin of main
