@@ -84,11 +84,6 @@ int g16_ctx_create(g16_ctx** out, int device, void* main_stream) {
         e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->hi, cudaStreamNonBlocking, hi);
     }
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
-        int lo = 0, hi = 0;
-        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->prio[i], cudaStreamNonBlocking, hi);
-    }
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_dig[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_hi, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
@@ -167,8 +162,6 @@ void g16_ctx_destroy(g16_ctx* ctx) {
     if (ctx->h_proof) cudaFreeHost(ctx->h_proof);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->hi) cudaStreamDestroy(ctx->hi);
-    for (int i = 0; i < 2; i++)
-        if (ctx->prio[i]) cudaStreamDestroy(ctx->prio[i]);
     if (ctx->ev_hi) cudaEventDestroy(ctx->ev_hi);
     for (int i = 0; i < 2; i++)
         if (ctx->ev_dig[i]) cudaEventDestroy(ctx->ev_dig[i]);
@@ -831,10 +824,6 @@ static int queue_wire_chains(g16_ctx* ctx, cudaStream_t root) {
     int nsplit = 0;
     for (int k = 0; k < nchains; k++) {
         cudaStream_t st0 = ctx->opt_serialize ? root : ctx->side[k];
-        // option chain_priority: the a and b_g1 MSMs -- whose results still go through a 1.3 ms single-lane scaling -- run on
-        // high-priority streams so that they end before the other chains and the scaling hides under those
-        if (!ctx->opt_serialize && ctx->opt_chain_priority && (chains[k][0].qi == Q_A || chains[k][0].qi == Q_B1))
-            st0 = ctx->prio[chains[k][0].qi == Q_A ? 0 : 1];
         if (!ctx->opt_serialize) G16_CUDA(ctx, cudaStreamWaitEvent(st0, ctx->ev_wfork, 0));
         // split chain: the MSM that reuses the digit stage starts on its own stream as soon as that stage exists, instead of
         // queueing behind the first MSM's point stage (a serial chain left the G2 MSM alone at the end of the proof)
@@ -1272,7 +1261,6 @@ int g16_set_option(g16_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "ntt_batch")) ctx->opt_ntt_batch = value;
     else if (!strcmp(key, "wm_priority")) ctx->opt_wm_priority = value;
     else if (!strcmp(key, "wm_first")) ctx->opt_wm_first = value;
-    else if (!strcmp(key, "chain_priority")) ctx->opt_chain_priority = value;
     else if (!strcmp(key, "verify_occupancy")) ctx->opt_verify_occupancy = value;
     else if (!strcmp(key, "asm_tables")) ctx->opt_asm_tables = value;
     else return set_err(ctx, G16_ERR_BAD_ARG, "unknown option '%s'", key);

@@ -190,8 +190,6 @@ struct g16_ctx {
     int opt_wm_priority = 0;   // witness map + h MSM on the internal high-priority stream
     int opt_wm_first = -1;     // the wire MSM chains start only when the witness map is done (it then runs alone);
                                // -1 = auto: for domains of 2^20 and more, 0 / 1 force
-    int opt_chain_priority = 0;  // the a and b_g1 chains on high-priority streams (their results still need the scaling kernel)
-    cudaStream_t prio[2] = {};
     cudaStream_t hi = nullptr;  // high-priority twin of main
     cudaEvent_t ev_dig[2] = {}, ev_hi = nullptr;
     bool share_al = false, share_b = false;  // l reuses a's digit stage / b_g2 reuses b_g1's
