@@ -251,7 +251,7 @@ class Runner:
                 "plan": ({"kind": args.plan, "witness_map_rank": plan.wm_rank, "witness_map_b_c_ranks": [plan.wm2_rank, plan.wm3_rank], "rank0_wire_share": round(plan.z_ranges[0][1] / max(m1, 1), 4),
                           "h_scatter_bytes_per_peer": plan.h_chunk * 32 if plan.staggered else 0} if self.world > 1 else None),
                 "l2": "inputs>L2 (pk+scratch ~GBs)", "precompute": args.precompute,
-                "window_bits": args.window_bits or "auto (19 at this size)", "ba_levels": args.ba_levels, "synthetic": SYNTH_NOTE}
+                "window_bits": args.window_bits or {"auto": {k: self.ctx.msm_stats(i)["window_bits"] for i, k in enumerate(("h", "l", "a", "b_g1", "b_g2"))}}, "ba_levels": args.ba_levels, "synthetic": SYNTH_NOTE}
 
 
 def timed(torch, dist, world, fn, steps, sampler=None):

@@ -327,8 +327,15 @@ int msm_pick_window(size_t n, int group, bool precomp) {
     if (!precomp) {
         c = (int)lg - 5;
         if (c > 16) c = 16;
-    } else {
+    } else if (lg < 17) {
         c = (int)lg - 1;
+    } else {
+        // with the window tables every digit of every point lands in ONE set of 2^(c-1) buckets, so a smaller window buys
+        // fuller buckets (the pairwise levels halve them more effectively, the bucket reduction shrinks) for ~1/c more
+        // (point, window) pairs.  Measured best at c = round(log2 n) - 3 from 2^17.6 to 2^21.5 points
+        // (profiles/r02_ab_shard_window*.log, r02_ab_window_n1.log: S-rs256 28.3 -> 26.3 ms, one rank of 8 5.42 -> 5.17 ms)
+        unsigned r = lg + ((double)n >= 1.41421356 * (double)((size_t)1 << lg) ? 1 : 0);  // log2 n, rounded
+        c = (int)r - 3;
         if (c > 20) c = 20;
     }
     if (c < 4) c = 4;
@@ -593,7 +600,7 @@ static int msm_point_stage(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Msm
 }
 
 int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st, cudaEvent_t ev0,
-            cudaEvent_t ev1, const MsmScratch* digits, cudaEvent_t ev_digits_done) {
+            cudaEvent_t ev1, const MsmScratch* digits, cudaEvent_t ev_digits_done, cudaEvent_t gate) {
     if (mb->group != 1 && mb->group != 2) return set_err(ctx, G16_ERR_BAD_ARG, "msm: bases not set");
     if (n > mb->n) return set_err(ctx, G16_ERR_BAD_ARG, "msm: %zu scalars for %zu bases", n, mb->n);
     if (n == 0 || mb->n == 0) {
@@ -607,6 +614,7 @@ int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, s
     } else if (digits->cap_items != sc->cap_items || digits->cap_buckets != sc->cap_buckets || digits->ba_levels != sc->ba_levels) {
         return set_err(ctx, G16_ERR_BAD_ARG, "msm: shared digit stage has a different geometry");
     }
+    if (gate) G16_CUDA(ctx, cudaStreamWaitEvent(st, gate, 0));  // the point stage may have to leave the multiplier to someone else
     if (mb->group == 1) return msm_point_stage<Fq>(ctx, mb, sc, digits, n, st, ev0, ev1);
     return msm_point_stage<Fq2>(ctx, mb, sc, digits, n, st, ev0, ev1);
 }

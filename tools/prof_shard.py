@@ -35,6 +35,8 @@ h_len = len(pk.arrays["h_query"])
 m1 = len(pk.arrays["a_query"]) - 1
 plan = sharded.staggered_plan(h_len, m1, args.world)
 rank = args.rank
+for kv in args.opt:   # window_bits / ba_levels act on bases loaded afterwards
+    ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 ctx.load_pk(pk.arrays, pk.encoding, rank, args.world, True, h_range=plan.h_ranges[rank], z_range=plan.z_ranges[rank])
 for kv in args.opt:
     ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
