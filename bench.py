@@ -106,9 +106,10 @@ def ncu_traffic(workload: str, witness: str, slots: int):
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(p) as f:
-            rec = json.load(f).get(f"{workload}/{witness}")
-        if rec and abs(rec["slots"] - slots) <= 0.001 * slots:
-            return float(rec["dram_read_bytes"] + rec["dram_write_bytes"]), rec.get("source")
+            recs = json.load(f).get(f"{workload}/{witness}") or []
+        for rec in (recs if isinstance(recs, list) else [recs]):   # one record per captured geometry (window)
+            if abs(rec["slots"] - slots) <= 0.001 * slots:
+                return float(rec["dram_read_bytes"] + rec["dram_write_bytes"]), rec.get("source")
     except Exception:
         pass
     return None, None

@@ -19,7 +19,8 @@ for k,v in ex.items():
     elif v: print('   extra', k, {kk: v.get(kk) for kk in ('ms_per_step','error','proof_verified_in_exponent')}, 'e2e', (v.get('e2e') or {}).get('ms_per_step'))
 "; }
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.log; echo "bench rc=$? $((SECONDS-t0))s"; tail -3 gpurun_out/bench_n1.log | cut -c1-250; show gpurun_out/bench_n1.json n1
-timeout 300 python bench.py --steps 20 --warmup 3 --extras '' --no-cpu-baseline --inflight 0 --opt wm_priority=2 > gpurun_out/bench_wmprio2.json 2> gpurun_out/bench_wmprio2.log; show gpurun_out/bench_wmprio2.json wm_priority2
+G16_LIB=$PWD/gpurun_variants/libg16_lb6.so timeout 300 python bench.py --steps 20 --warmup 3 --extras '' --no-cpu-baseline --inflight 0 > gpurun_out/bench_lb6.json 2> gpurun_out/bench_lb6.log; show gpurun_out/bench_lb6.json k_ba_add_80regs_6blocks
+timeout 300 python bench.py --steps 20 --warmup 3 --extras '' --no-cpu-baseline --inflight 0 > gpurun_out/bench_lb5.json 2> gpurun_out/bench_lb5.log; show gpurun_out/bench_lb5.json k_ba_add_92regs_5blocks
 timeout 300 python bench.py --steps 20 --warmup 3 --extras '' --no-cpu-baseline --inflight 0 --witness circom > gpurun_out/bench_circom.json 2> gpurun_out/bench_circom.log; show gpurun_out/bench_circom.json circom
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.log; echo "reference rc=$? $((SECONDS-t0))s"; tail -2 gpurun_out/bench_reference.log; cut -c1-400 gpurun_out/bench_reference.json
 timeout 900 python tools/sweep.py > gpurun_out/sweep_n1.jsonl 2> gpurun_out/sweep_n1.log; echo "sweep rc=$? $((SECONDS-t0))s"; python -c "
