@@ -277,13 +277,10 @@ __device__ __forceinline__ void ba_add_pair(Affine<F>& p1, const Affine<F>& p2, 
     p1.x = x3;
 }
 
-#ifdef G16_BA_LB6  // A/B: hold the G1 instance to 80 registers (6 blocks per SM, 36 bytes spilled) instead of 92 (5 blocks)
-#define G16_BA_ADD_BOUNDS __launch_bounds__(128, sizeof(F) == sizeof(Fq) ? 6 : 3)
-#else
-#define G16_BA_ADD_BOUNDS __launch_bounds__(128)
-#endif
+// G1 held to 80 registers (6 blocks per SM, 36 bytes spilled) rather than the 92 ptxas would take (5 blocks): h-query level 0
+// 1.537 against 1.554 ms (profiles/r02_final_pass2.log); G2 to 168 (3 blocks)
 template <class F, bool L0>
-__global__ void G16_BA_ADD_BOUNDS
+__global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fq) ? 6 : 3)
     k_ba_add(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ in_start,
              const uint32_t* __restrict__ in_cnt, const uint32_t* __restrict__ out_off, size_t nbuckets,
              const uint32_t* __restrict__ tb_last, const Fq* __restrict__ pre, const Fq* __restrict__ Tinv,
