@@ -91,7 +91,6 @@ int g16_ctx_create(g16_ctx** out, int device, void* main_stream) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_wfork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_wire_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_gate, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_proof, 512, cudaHostAllocDefault);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_scale[i], cudaEventDisableTiming);
     for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev_t[i]);
@@ -160,7 +159,6 @@ void g16_ctx_destroy(g16_ctx* ctx) {
     if (ctx->ev_wfork) cudaEventDestroy(ctx->ev_wfork);
     if (ctx->ev_wire_done) cudaEventDestroy(ctx->ev_wire_done);
     if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
-    if (ctx->ev_gate) cudaEventDestroy(ctx->ev_gate);
     if (ctx->h_proof) cudaFreeHost(ctx->h_proof);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->hi) cudaStreamDestroy(ctx->hi);
@@ -854,7 +852,7 @@ static int queue_wire_chains(g16_ctx* ctx, cudaStream_t root) {
             G16_TRY(rec_t(ctx, ctx->ev_t[2 + 2 * qi], st));
             if (split && j == 0 && cnt == 0) G16_CUDA(ctx, cudaEventRecord(ctx->ev_dig[split_slot], st));  // nothing to build
             G16_TRY(msm_run(ctx, &ctx->q[qi], &ctx->scratch[qi], sc, cnt, st, ea0, ea1, from >= 0 ? &ctx->scratch[from] : nullptr,
-                            split && j == 0 ? ctx->ev_dig[split_slot] : nullptr, ctx->wire_gate));
+                            split && j == 0 ? ctx->ev_dig[split_slot] : nullptr));
             const bool have = cnt && ctx->scratch[qi].result;
             // s * MSM_a and r * MSM_b1 are ~1.6 ms single-lane chains: they get their own streams so that neither the next
             // MSM of this chain nor anything else waits for them; they finish beside the MSMs still in flight
@@ -910,23 +908,20 @@ static int shard_begin(g16_ctx* ctx, int reduction, bool run_wm, bool allow_hi =
     // chains run (and end) together instead of the h MSM finishing alone behind the others
     // (measured: S-rs256 29.0 -> 28.2 ms; S-2^12 1.86 -> 2.16 ms and S-2^16 3.06 -> 3.43 ms, where the map is a fraction of a
     // millisecond and delaying the chains only adds latency -- hence automatic from n = 2^20 on: profiles/r02_ab_sched2_glv.log)
-    // wm_first = 2: only the POINT stages wait for the map; the digit stages (scalar recoding + pair sort, bound by memory)
-    // run beside the transforms (bound by the multiplier).  The gate is an event inside one capture, so only the one-GPU
-    // proof (allow_hi), where map and chains are queued by the same call, takes this form.
-    const int first_mode = ctx->opt_wm_first < 0 ? (ctx->log_n >= 20 ? 1 : 0) : ctx->opt_wm_first;
-    const bool wm_first = run_wm && first_mode != 0 && !ctx->opt_serialize && busy;
-    const bool gated = wm_first && first_mode == 2 && allow_hi && wire != main;
-    auto start_wire = [&](bool fork_here) -> int {
+    // (letting only the POINT stages wait for the map, with the digit stages beside it, was measured too: sort and transforms
+    // slow each other down, 28.3 -> 28.8-30.7 ms: profiles/r02_ab_gate.log)
+    const bool want_first = ctx->opt_wm_first < 0 ? ctx->log_n >= 20 : ctx->opt_wm_first != 0;
+    const bool wm_first = run_wm && want_first && !ctx->opt_serialize && busy;
+    auto start_wire = [&]() -> int {
         if (wire != main) {
-            if (fork_here) G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
+            G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
             G16_CUDA(ctx, cudaStreamWaitEvent(wire, ctx->ev_fork, 0));
         }
-        G16_TRY(run_graphed(ctx, GR_WIRE, 0x57 + (gated ? 0x1000 : 0), wire, [&] { return queue_wire_chains(ctx, wire); }));
+        G16_TRY(run_graphed(ctx, GR_WIRE, 0x57, wire, [&] { return queue_wire_chains(ctx, wire); }));
         if (wire != main) G16_CUDA(ctx, cudaEventRecord(ctx->ev_wire_done, wire));
         return G16_OK;
     };
-    if (!wm_first) G16_TRY(start_wire(true));
-    if (gated) G16_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));  // the chains fork from BEFORE the map
+    if (!wm_first) G16_TRY(start_wire());
     // main: witness map (r1cs_to_qap.rs:150-213)
     // (option wm_priority: on the high-priority twin of main, so that the h MSM -- which can only start afterwards -- is not
     // pushed to the end of the proof by the four z-only MSMs already in flight)
@@ -951,15 +946,7 @@ static int shard_begin(g16_ctx* ctx, int reduction, bool run_wm, bool allow_hi =
         G16_TRY(rec_t(ctx, ctx->ev_t[0], ws));
         G16_TRY(rec_t(ctx, ctx->ev_t[1], ws));
     }
-    if (wm_first) {
-        if (gated) {
-            G16_CUDA(ctx, cudaEventRecord(ctx->ev_gate, ws));
-            ctx->wire_gate = ctx->ev_gate;
-        }
-        int rc = start_wire(!gated);
-        ctx->wire_gate = nullptr;
-        G16_TRY(rc);
-    }
+    if (wm_first) G16_TRY(start_wire());
     return G16_OK;
 }
 

@@ -131,8 +131,7 @@ struct g16_ctx {
     cudaStream_t side[g16::kSideStreams] = {};
     cudaEvent_t ev_fork = nullptr;
     cudaStream_t wire = nullptr;  // root of the z-only MSM chains (forked from main, joined back at the end of a shard run)
-    cudaEvent_t ev_wfork = nullptr, ev_wire_done = nullptr, ev_pre = nullptr, ev_gate = nullptr;
-    cudaEvent_t wire_gate = nullptr;  // set while queueing wire chains whose point stages wait for the witness map (wm_first = 2)
+    cudaEvent_t ev_wfork = nullptr, ev_wire_done = nullptr, ev_pre = nullptr;
     g16::GraphSlot graphs[8];     // FULL / WIRE / WM / H launch sequences, WM parts A / B / C / FINAL
     uint64_t graph_epoch = 1;     // bumped by everything that changes a sequence (options, key, R1CS)
     bool capturing = false;
@@ -284,8 +283,7 @@ void msm_free(MsmBases* mb, MsmScratch* sc);
 // n / window / table geometry and skip pattern (msm_can_share): its sorted references and task lists are reused.
 int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st,
             cudaEvent_t ev_acc0 = nullptr, cudaEvent_t ev_acc1 = nullptr, const MsmScratch* digits = nullptr,
-            cudaEvent_t ev_digits_done = nullptr,  // recorded on st once the digit stage this call built is complete
-            cudaEvent_t gate = nullptr);           // waited for on st between the digit stage and the point stage
+            cudaEvent_t ev_digits_done = nullptr);  // recorded on st once the digit stage this call built is complete
 // true when MSMs over `b` may reuse the digit stage of `a` (same geometry; every point `a` skips is infinity in `b` too
 // and `b` has at most `max_extra_inf` further points at infinity).  Synchronises the stream.
 int msm_can_share(g16_ctx* ctx, const MsmBases* a, const MsmBases* b, size_t max_extra_inf, bool* ok, cudaStream_t st);

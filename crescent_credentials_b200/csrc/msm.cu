@@ -600,7 +600,7 @@ static int msm_point_stage(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Msm
 }
 
 int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, size_t n, cudaStream_t st, cudaEvent_t ev0,
-            cudaEvent_t ev1, const MsmScratch* digits, cudaEvent_t ev_digits_done, cudaEvent_t gate) {
+            cudaEvent_t ev1, const MsmScratch* digits, cudaEvent_t ev_digits_done) {
     if (mb->group != 1 && mb->group != 2) return set_err(ctx, G16_ERR_BAD_ARG, "msm: bases not set");
     if (n > mb->n) return set_err(ctx, G16_ERR_BAD_ARG, "msm: %zu scalars for %zu bases", n, mb->n);
     if (n == 0 || mb->n == 0) {
@@ -614,7 +614,6 @@ int msm_run(g16_ctx* ctx, MsmBases* mb, MsmScratch* sc, const Fr* scalars_dev, s
     } else if (digits->cap_items != sc->cap_items || digits->cap_buckets != sc->cap_buckets || digits->ba_levels != sc->ba_levels) {
         return set_err(ctx, G16_ERR_BAD_ARG, "msm: shared digit stage has a different geometry");
     }
-    if (gate) G16_CUDA(ctx, cudaStreamWaitEvent(st, gate, 0));  // the point stage may have to leave the multiplier to someone else
     if (mb->group == 1) return msm_point_stage<Fq>(ctx, mb, sc, digits, n, st, ev0, ev1);
     return msm_point_stage<Fq2>(ctx, mb, sc, digits, n, st, ev0, ev1);
 }

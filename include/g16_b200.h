@@ -212,14 +212,14 @@ int g16_get_timings(g16_ctx* ctx, g16_timings* out);
 /* Options: "serialize" = 1 runs every stage on the main stream (no overlap; for per-kernel timing),
  * "kernel_events" = 1 brackets the bucket accumulation of every MSM (batched-affine levels + XYZZ tail) with CUDA events
  *   (fills g16_timings.acc_ms); = 2 brackets only the first level's k_ba_add launch (the dominant kernel),
- * "window_bits" = c forces the Pippenger window of bases loaded afterwards (0 = automatic),
+ * "window_bits" = c forces the Pippenger window of bases loaded afterwards (0 = automatic: round(log2 n) - 3 with window tables
+ *   from 2^17 points on, log2 n - 1 below, log2 n - 5 capped at 16 without tables),
  * "ba_levels" = L runs L pairwise batched-affine levels before the XYZZ tail for bases loaded afterwards (-1 = default 5,
  *   0 = XYZZ only), "share_digits" = 0 disables the reuse of one digit stage by a/l and b_g1/b_g2,
  * "split_chains" = 0 queues the MSM that reuses a digit stage behind the one that built it (default 1: beside it),
  * "wm_priority" = 1 runs the witness map and the h MSM on a high-priority stream, = 2 only the witness map (default 0),
- * "wm_first" = 1 / 0 starts the z-only MSM chains only after the witness map, which then runs alone / beside it; = 2 lets
- *   their digit stages (recoding + sort) run beside the map and holds back only the point stages (one-GPU proof only;
- *   default -1: 1 for domains of 2^20 and more, else 0),
+ * "wm_first" = 1 / 0 starts the z-only MSM chains only after the witness map, which then runs alone / beside it (default -1:
+ *   after it for domains of 2^20 and more),
  * "ntt_radix4" = 0 / 1 forces the radix-2 / radix-4 transform passes (default -1: radix-4 only when no MSM runs beside),
  * "spmv_sell" = 0 selects the row-per-thread CSR kernel instead of the sliced-ELL one (default 1),
  * "ntt_batch" = 0 / 1 forces one launch per transform and pass / batched launches for the witness map (default -1: batched

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2: wm_first = 2 (digit stages of the z-only MSMs beside the witness map, point stages after it) against wm_first = 1.
+# Round 2 (historical: the gated variant was removed afterwards): wm_first = 2 (digit stages of the z-only MSMs beside the witness map, point stages after it) against wm_first = 1.
 set -u
 mkdir -p gpurun_out
 t0=$SECONDS
