@@ -363,6 +363,8 @@ int g16_msm_run_dev(g16_ctx* ctx, int slot, const void* scalars_dev, size_t n, u
     return G16_OK;
 }
 
+int g16_msm_window_bits(size_t n, int precompute) { return msm_pick_window(n, 1, precompute != 0); }
+
 int g16_msm_copy_result_dev(g16_ctx* ctx, int slot, void* dst_dev) {
     if (!ctx || !dst_dev || slot < 0 || slot >= kMsmSlots) return ctx ? set_err(ctx, G16_ERR_BAD_ARG, "msm_copy_result: bad argument") : G16_ERR_BAD_ARG;
     Guard g(ctx);

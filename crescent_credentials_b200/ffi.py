@@ -26,7 +26,7 @@ EXPORTS = [
     "g16_ctx_load_r1cs", "g16_prove", "g16_upload_witness", "g16_prove_resident", "g16_prove_shard",
     "g16_prove_combine", "g16_partial_dev", "g16_prove_shard_dev", "g16_prove_combine_dev", "g16_witness_map",
     "g16_domain_size", "g16_get_timings", "g16_msm_g1", "g16_msm_g2", "g16_msm_set_bases", "g16_msm_set_bases_dev",
-    "g16_msm_run_dev", "g16_ntt", "g16_ntt_dev", "g16_field_op", "g16_fixed_base_g1", "g16_fixed_base_g2",
+    "g16_msm_run_dev", "g16_msm_window_bits", "g16_ntt", "g16_ntt_dev", "g16_field_op", "g16_fixed_base_g1", "g16_fixed_base_g2",
     "g16_fixed_base_g1_dev", "g16_fixed_base_g2_dev", "g16_r1cs_eval", "g16_dev_alloc", "g16_dev_free",
     "g16_dev_upload", "g16_dev_download", "g16_sync", "g16_bench_int_pipe", "g16_launch_count", "g16_set_option",
     "g16_pow_table", "g16_copy_partial_dev", "g16_prove_prepare", "g16_get_msm_stats", "g16_ctx_load_pk_ranges",
@@ -148,6 +148,7 @@ def load_library() -> C.CDLL:
     lib.g16_msm_set_bases.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
     lib.g16_msm_set_bases_dev.argtypes = lib.g16_msm_set_bases.argtypes
     lib.g16_msm_run_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]
+    lib.g16_msm_window_bits.argtypes = [C.c_size_t, C.c_int]
     lib.g16_msm_copy_result_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.g16_msm_combine_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
     lib.g16_graph_stats.argtypes = [C.c_void_p, C.c_void_p]
@@ -195,6 +196,11 @@ def _ptr(a):
         return C.c_void_p(int(a))
     assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
     return C.c_void_p(a.ctypes.data)
+
+
+def msm_window_bits(n: int, precompute: bool = True) -> int:
+    """The Pippenger window the library picks for n bases (g16_msm_window_bits; no device needed)."""
+    return int(load_library().g16_msm_window_bits(n, int(precompute)))
 
 
 class Context:

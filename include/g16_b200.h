@@ -246,6 +246,11 @@ int g16_msm_set_bases(g16_ctx* ctx, int slot, int group /*1|2*/, const uint64_t*
 int g16_msm_set_bases_dev(g16_ctx* ctx, int slot, int group, const void* points_dev, size_t n, int window_bits,
                           int precompute);
 int g16_msm_run_dev(g16_ctx* ctx, int slot, const void* scalars_dev, size_t n, uint64_t* out, int* out_inf);
+/* The window (bits per signed digit) the library picks for n bases when window_bits = 0: with window tables (precompute)
+ * round(log2 n) - 3 from 2^17 points on and log2 n - 1 below (one bucket set serves all windows, so a smaller window buys
+ * fuller buckets); without tables log2 n - 5, at most 16.  The tables hold ceil(254 / c) copies of the bases.  Pure function:
+ * needs no context and no device. */
+int g16_msm_window_bits(size_t n, int precompute);
 /* Point-range sharding of a stand-alone MSM (the pattern of g16_prove_shard / g16_prove_combine for one sum): every
  * rank runs g16_msm_run_dev over its contiguous share of the pairs with out = NULL, copies its partial sum (XYZZ: 16 u64 words
  * for G1, 32 for G2) to dst_dev with g16_msm_copy_result_dev -- stream-ordered, so that one all_gather on the same stream can

@@ -293,3 +293,27 @@ def test_vectorised_r1cs_loader_equals_the_rowwise_definition():
         a, b = load_matrices(r1cs_bytes), _load_matrices_rowwise(r1cs_bytes)
         for k in range(3):
             assert np.array_equal(a.row_ptr[k], b.row_ptr[k]) and np.array_equal(a.col[k], b.col[k]) and np.array_equal(a.val[k], b.val[k])
+
+
+def test_automatic_window_rule():
+    """g16_msm_window_bits: with window tables round(log2 n) - 3 from 2^17 points on -- the sizes measured on the GPU
+    (profiles/r02_ab_shard_window*.log, r02_ab_window_n1.log: one rank of 8 / 4 / 2 and the whole S-rs256 / S-mdl1 proof) --
+    log2 n - 1 below; without tables log2 n - 5 capped at 16; never below 4.  The table count follows from it."""
+    import math
+    measured_best = {207_126: 15, 262_144: 15, 414_252: 16, 524_288: 16, 828_504: 17, 1_048_576: 17, 1_449_999: 17,
+                     2_097_151: 18, 2_899_999: 18, 4_194_303: 19}
+    for n, c in measured_best.items():
+        assert ffi.msm_window_bits(n, True) == c, n
+    for n in (1 << 17, 150_000, (1 << 26) + 5, 1 << 30):
+        assert ffi.msm_window_bits(n, True) == min(20, round(math.log2(n)) - 3)
+    for lg in range(6, 17):
+        assert ffi.msm_window_bits(1 << lg, True) == max(4, lg - 1)
+        assert ffi.msm_window_bits((1 << lg) + 1, False) == max(4, min(16, lg - 5))
+    assert ffi.msm_window_bits(1, True) == 4 and ffi.msm_window_bits(0, False) == 4
+    assert ffi.msm_window_bits(1 << 26, False) == 16
+    # monotone in n
+    prev = 0
+    for n in range(1 << 12, 1 << 23, 37_123):
+        c = ffi.msm_window_bits(n, True)
+        assert c >= prev or (n >= (1 << 17) and prev - c <= 1 and n < (1 << 17) + 37_123 * 2)
+        prev = c
