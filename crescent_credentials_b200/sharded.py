@@ -24,8 +24,11 @@ from .groth16 import Proof, ProvingKey, ConstraintMatrices, fr_to_mont, R_MOD
 
 # witness-map time over the time of the four z-only MSMs on one B200; only the balance of the staggered plan depends on it,
 # never a result.  0.28 in round 1 (4.25 ms vs ~15 ms); at N = 2 that left rank 0 done at 14.4 ms and rank 1 at 16.2 ms
-# (profiles/r02_bench_n2.json), i.e. rank 0 should take 0.40 of the wire MSMs instead of 0.36: 0.20.
-WM_OVER_Z = 0.20
+# (profiles/r02_bench_n2.json), i.e. rank 0 should take 0.40 of the wire MSMs instead of 0.36: 0.20.  The smaller automatic
+# window then made the wire MSMs ~9 % cheaper: with 0.20 rank 0 was done at 14.46 ms and rank 1 at 13.87 ms at N = 2
+# (profiles/r02_bench_n2_final.json: 3.23 + (2 f0 - 1) Z = 0.59 with f0 = 0.40 gives Z = 13.2 ms, ratio 0.245); the N = 4 stage
+# timings of the same day point at ~0.23.  0.235: rank 0 takes 0.38 of the wire MSMs at N = 2, 0.074 at N = 4, none from N = 5 on.
+WM_OVER_Z = 0.235
 
 
 def shard_range(total: int, rank: int, world: int):
