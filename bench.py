@@ -67,7 +67,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -366,13 +366,14 @@ def main():
 
     launches0 = ctx.launch_count()
     # ---- timed region 1: witness resident (the `value`) ---------------------------------------------------------
+    # (clocks and throttle reasons are sampled across BOTH timed regions: at 8 GPUs one of them is only ~0.1 s long)
     with ClockSampler(local_rank) as clk:
         ms_res = timed(torch, dist, world, run.step_resident, args.steps)
-    launches = ctx.launch_count() - launches0
-    graph_stats = ctx.graph_stats()   # launches replayed as CUDA graphs count as the kernels they stand for
-    stage = ctx.timings() if world == 1 else {}
-    # ---- timed region 2: end to end through the public call, host witness -------------------------------------------
-    ms_e2e = timed(torch, dist, world, run.step_e2e, args.steps)
+        launches = ctx.launch_count() - launches0
+        graph_stats = ctx.graph_stats()   # launches replayed as CUDA graphs count as the kernels they stand for
+        stage = ctx.timings() if world == 1 else {}
+        # ---- timed region 2: end to end through the public call, host witness ---------------------------------------
+        ms_e2e = timed(torch, dist, world, run.step_e2e, args.steps)
     # ---- timed region 3 (1 GPU only): several proofs in flight ---------------------------------------------------------
     # A lone proof ends with latency-bound tails (shared inversions, bucket reduction, assembly) during which most SMs idle.
     # A prover that serves a queue keeps a second proof in flight on its own context (own streams and scratch), whose
