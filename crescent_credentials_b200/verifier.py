@@ -178,3 +178,41 @@ class Verifier:
         if not batched and (v == ffi.VERDICT_UNEXPECTED_IDENTITY).any():
             raise UnexpectedIdentity()
         return [bool(t == ffi.VERDICT_ACCEPT) for t in v]
+
+
+def verify_proofs_replicated(verifier, pvk, proofs: Sequence, public_inputs: Sequence, rank: int, world: int,
+                             device=None) -> List[bool]:
+    """Verification over several GPUs.  The unit of work is one (proof, inputs) pair and pairs are independent (verifier.rs:44-65
+    reads nothing but the pair and the key), so there is no exchange step to put a collective on: every rank is a replica
+    holding the same prepared key, verifies the contiguous slice shard_range(n, rank, world) of the batch on its own GPU with
+    `verifier.verify_proofs`, and ONE all_gather of the verdict bytes (n bytes in total) hands every rank the full list in
+    proof order.  Call collectively (torch.distributed initialised; `device` = where the gathered tensor lives: the rank's
+    CUDA device under NCCL, None / "cpu" under gloo)."""
+    import torch
+    import torch.distributed as dist
+    from .sharded import shard_range
+    n = len(proofs)
+    if n != len(public_inputs):
+        raise ffi.G16Error(ffi.ERR_BAD_ARG, "one public-input vector per proof")
+    if world <= 1:
+        return verifier.verify_proofs(pvk, proofs, public_inputs)
+    lo, hi = shard_range(n, rank, world)
+    mine = verifier.verify_proofs(pvk, proofs[lo:hi], public_inputs[lo:hi]) if hi > lo else []
+    chunk = -(-n // world) if n else 0          # slices differ by at most one pair: pad to the longest
+    if chunk == 0:
+        return []
+    buf = torch.full((chunk,), 255, dtype=torch.uint8)
+    if mine:
+        buf[:len(mine)] = torch.tensor([1 if v else 0 for v in mine], dtype=torch.uint8)
+    buf = buf.to(device) if device is not None else buf
+    out = torch.empty((world * chunk,), dtype=torch.uint8, device=buf.device)
+    dist.all_gather_into_tensor(out, buf)
+    out = out.cpu().view(world, chunk)
+    verdicts: List[bool] = []
+    for r in range(world):
+        rlo, rhi = shard_range(n, r, world)
+        row = out[r, :rhi - rlo].tolist()
+        if any(v > 1 for v in row):
+            raise ffi.G16Error(ffi.ERR_BAD_ARG, f"rank {r} returned no verdict for part of its slice")
+        verdicts += [v == 1 for v in row]
+    return verdicts

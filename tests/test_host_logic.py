@@ -317,3 +317,60 @@ def test_automatic_window_rule():
         c = ffi.msm_window_bits(n, True)
         assert c >= prev or (n >= (1 << 17) and prev - c <= 1 and n < (1 << 17) + 37_123 * 2)
         prev = c
+
+
+class _StubVerifier:
+    """Stands in for verifier.Verifier on a CPU box: accepts a 'proof' iff it is an even number; records what it was given."""
+
+    def __init__(self):
+        self.seen = []
+
+    def verify_proofs(self, pvk, proofs, public_inputs):
+        assert len(proofs) == len(public_inputs) and all(x == [p, p + 1] for p, x in zip(proofs, public_inputs))
+        self.seen += list(proofs)
+        return [p % 2 == 0 for p in proofs]
+
+
+def _gloo_verify_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from crescent_credentials_b200.verifier import verify_proofs_replicated
+    got = {}
+    for n in (0, 1, 2, 5, 16, 17):
+        v = _StubVerifier()
+        proofs = [7 * i + 3 for i in range(n)]
+        out = verify_proofs_replicated(v, None, proofs, [[p, p + 1] for p in proofs], rank, world)
+        got[n] = (out, v.seen)
+    q.put((rank, got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_replicated_verification_partitions_by_proof(world):
+    """verifier.verify_proofs_replicated over gloo: every rank verifies only its slice, every rank ends with the full verdict
+    list in proof order (uneven and empty slices included)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_gloo_verify_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for n in (0, 1, 2, 5, 16, 17):
+        proofs = [7 * i + 3 for i in range(n)]
+        seen_all = []
+        for r in range(world):
+            out, seen = res[r][n]
+            assert out == [p % 2 == 0 for p in proofs], (n, r)
+            lo, hi = shard_range(n, r, world)
+            assert seen == proofs[lo:hi]
+            seen_all += seen
+        assert seen_all == proofs
