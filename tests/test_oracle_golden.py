@@ -296,3 +296,40 @@ def test_cpu_instance_builder_is_satisfied_and_deterministic():
     assert g.fr_from_mont(c.field_op(0, 8, x, g.fr_to_mont([7]))) == [21, 35, (o.R_MOD - 7) % o.R_MOD]
     assert g.fr_from_mont(c.field_op(0, 9, x, g.fr_to_mont([7]))) == [10, 12, 6]
     assert g.fr_from_mont(c.pow_table(g.fr_to_mont([3])[0], g.fr_to_mont([2])[0], 70)) == [2 * pow(3, i, o.R_MOD) % o.R_MOD for i in range(70)]
+
+
+def test_bench_exponent_check_is_not_vacuous():
+    """bench.check_proof_in_exponent (the gate in front of every bench number) on a CPU-built instance and key: it accepts the
+    oracle's proof and rejects (i) a proof whose C carries a wrong h -- one coefficient off, every MSM right: the case the
+    round-1 check let through because it took h(t)Z(t) from the prover's own h --, (ii) a proof for another witness,
+    (iii) a proof made with another r."""
+    import sys
+    import types
+    import refsynth
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    inst = refsynth.make_instance_cpu("S-2^12", seed=0x5A0CE)
+    td = types.SimpleNamespace(**bench.TRAPDOOR)
+    arrays, qap = refsynth.generate_parameters_cpu(inst, td)
+    r_int, s_int = bench.R_INT % o.R_MOD, bench.S_INT % o.R_MOD
+    r_m, s_m = g.fr_to_mont([r_int])[0], g.fr_to_mont([s_int])[0]
+    r1, pk = refsynth.r1cs_of(inst), c.pk_struct(arrays)
+
+    def proof_of(z_mont, r_mont):
+        pr, _, _ = c.prove(pk, r1, z_mont, r_mont, s_m, threads=4)
+        return g.Proof(g.g1_from_mont(pr[0]), g.g2_from_mont(pr[1]), g.g1_from_mont(pr[2]))
+
+    good = proof_of(inst.z_mont, r_m)
+    assert bench.check_proof_in_exponent(good, inst, qap, td, r_int, s_int)
+    # (i) h[5] off by one: C moves by h_query[5], A and B stay right
+    wrong_h = g.Proof(good.a, good.b, o.G1.add(good.c, g.g1_from_mont(arrays["h_query"][5])))
+    assert not bench.check_proof_in_exponent(wrong_h, inst, qap, td, r_int, s_int)
+    # (ii) another (still satisfying) witness is another proof: rebuild the instance from another seed, prove it under its
+    # own key, check it against THIS instance
+    other = refsynth.make_instance_cpu("S-2^12", seed=0x5A0CF)
+    arrays2, _ = refsynth.generate_parameters_cpu(other, td)
+    pr2, _, _ = c.prove(c.pk_struct(arrays2), refsynth.r1cs_of(other), other.z_mont, r_m, s_m, threads=4)
+    foreign = g.Proof(g.g1_from_mont(pr2[0]), g.g2_from_mont(pr2[1]), g.g1_from_mont(pr2[2]))
+    assert not bench.check_proof_in_exponent(foreign, inst, qap, td, r_int, s_int)
+    # (iii) another r
+    assert not bench.check_proof_in_exponent(proof_of(inst.z_mont, g.fr_to_mont([r_int + 1])[0]), inst, qap, td, r_int, s_int)
