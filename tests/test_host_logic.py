@@ -374,3 +374,20 @@ def test_replicated_verification_partitions_by_proof(world):
             assert seen == proofs[lo:hi]
             seen_all += seen
         assert seen_all == proofs
+
+
+def test_bench_traffic_records_match_by_geometry():
+    """bench.ncu_traffic: `roofline.traffic` comes from the committed ncu capture whose slot count is this run's (one record
+    per window geometry); any other geometry reads as no capture (null in the bench line), never a scaled guess."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    recs = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["S-rs256/uniform"]
+    assert isinstance(recs, list) and len(recs) >= 2
+    for rec in recs:
+        got, src = bench.ncu_traffic("S-rs256", "uniform", rec["slots"])
+        assert got == rec["dram_read_bytes"] + rec["dram_write_bytes"] and src == rec["source"]
+        assert os.path.exists(os.path.join(ROOT, src.split(":")[0])), src     # the capture summary it cites is committed
+        assert 232 * rec["slots"] < got < 2 * 232 * rec["slots"]                # above the algorithmic bytes, below 2x
+    assert bench.ncu_traffic("S-rs256", "uniform", recs[0]["slots"] * 2) == (None, None)
+    assert bench.ncu_traffic("S-mdl1", "uniform", recs[0]["slots"]) == (None, None)
