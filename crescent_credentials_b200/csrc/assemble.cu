@@ -177,7 +177,6 @@ __global__ void __launch_bounds__(160) k_assemble_pre_tables(const AsmTables* __
     }
 }
 
-// out = k * in for one G1 point (one lane; latency-bound, runs beside the remaining MSMs)
 // out = k * in for one G1 point (latency-bound, runs beside the remaining MSMs; exposed at the very end of a proof when the a /
 // b_g1 MSMs are the last to finish).  Two warps, one lane each: k = k1 + k2 * lambda, warp 0 computes k1 * P, warp 1 k2 * phi(P)
 // (glv.cuh), lane 0 adds.  `which` = 0: k = r, 1: k = s.
