@@ -391,3 +391,19 @@ def test_bench_traffic_records_match_by_geometry():
         assert 232 * rec["slots"] < got < 2 * 232 * rec["slots"]                # above the algorithmic bytes, below 2x
     assert bench.ncu_traffic("S-rs256", "uniform", recs[0]["slots"] * 2) == (None, None)
     assert bench.ncu_traffic("S-mdl1", "uniform", recs[0]["slots"]) == (None, None)
+
+
+def test_bench_whole_prove_budget_is_the_surveys():
+    """bench.survey_prove_budget / whole_prove_roofline: SURVEY 8d's per-proof budget for S-rs256 -- (2.1 + 4.35) M G1 points x 160
+    + 1.45 M G2 points x 480 = 1.73 G Fq products, 0.17 G Fr products, >= ~27 ms at 70 G mul/s -- and the fraction arithmetic."""
+    sys.path.insert(0, ROOT)
+    import bench
+    b = bench.survey_prove_budget(1 << 21, 1_450_000, 24, 16_047_951)
+    assert abs(b["fq_mul"] - 1.73e9) < 0.01e9 and abs(b["fr_mul"] - 0.177e9) < 0.01e9
+    assert 26.5 < b["mul"] / 70e9 * 1e3 < 27.5
+    cfg = {"domain": 1 << 21, "wires": 1_450_000, "nnz": 16_047_951}
+    w = bench.whole_prove_roofline(cfg, 24, 26.0, 65.0, 1)
+    assert abs(w["algorithmic_gmul_per_s"] - b["mul"] / 26.0e-3 / 1e9) < 1e-6
+    assert abs(w["frac_of_mul_peak"] - w["algorithmic_gmul_per_s"] / 65.0) < 1e-12 and 1.0 < w["frac_of_mul_peak"] < 1.2
+    assert abs(bench.whole_prove_roofline(cfg, 24, 26.0, 65.0, 8)["frac_of_mul_peak"] * 8 - w["frac_of_mul_peak"]) < 1e-12
+    assert bench.whole_prove_roofline(cfg, 24, 26.0, None, 1)["frac_of_mul_peak"] is None
